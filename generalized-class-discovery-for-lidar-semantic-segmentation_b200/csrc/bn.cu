@@ -1,0 +1,333 @@
+// bn.cu — batch norm over the rows of F [N, C] fused with ReLU and the residual add of a
+// BasicBlock, forward and backward.  Pure HBM-bound passes: every kernel reads each operand
+// once with 128-bit (fp32) / 64-bit (bf16) vector accesses and keeps per-channel reductions in
+// registers -> shared memory -> one fp64 atomic per channel per block.
+#include "common.cuh"
+
+namespace gcd {
+namespace {
+constexpr int kRedX = 32, kRedY = 8;        // reduction kernels: 32 channel lanes x 8 row lanes
+constexpr int kMaxChanIter = 16;            // supports up to 512 channels
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t; t.x = *reinterpret_cast<unsigned*>(&a); t.y = *reinterpret_cast<unsigned*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+// Generic two-quantity column reduction.  F(row, ch) -> (a, b); sums[ch] += a, sums[c + ch] += b.
+template <typename F>
+__device__ __forceinline__ void column_reduce2(int64_t n, int c, double* __restrict__ sums, F f) {
+  __shared__ float red_a[kRedY][kRedX + 1], red_b[kRedY][kRedX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int cb = 0; cb < c; cb += kRedX) {
+    const int ch = cb + tx;
+    float sa = 0.f, sb = 0.f;
+    if (ch < c)
+      for (int64_t r = (int64_t)blockIdx.x * kRedY + ty; r < n; r += (int64_t)gridDim.x * kRedY) {
+        float a, b;
+        f(r, ch, a, b);
+        sa += a; sb += b;
+      }
+    red_a[ty][tx] = sa; red_b[ty][tx] = sb;
+    __syncthreads();
+    if (ty == 0 && ch < c) {
+      float ta = 0.f, tb = 0.f;
+#pragma unroll
+      for (int j = 0; j < kRedY; ++j) { ta += red_a[j][tx]; tb += red_b[j][tx]; }
+      atomicAdd(&sums[ch], (double)ta);
+      atomicAdd(&sums[c + ch], (double)tb);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRedX* kRedY) bn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, double* __restrict__ stats) {
+  column_reduce2(n, c, stats, [&](int64_t r, int ch, float& a, float& b) {
+    const float v = to_f32<T>(x[r * ld + ch]);
+    a = v; b = v * v;
+  });
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t n, int c, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
+  const double m = stats[ch] * inv_n;
+  double var = stats[c + ch] * inv_n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[ch] = (float)m;
+  invstd[ch] = is;
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  scale[ch] = g * is;
+  shift[ch] = b - (float)m * g * is;
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_fold_eval_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                    float* __restrict__ scale, float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float is = 1.f / sqrtf(rv[ch] + eps);
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  scale[ch] = g * is;
+  shift[ch] = b - rm[ch] * g * is;
+}
+
+// y = act(x*scale + shift + residual); one thread per 4 consecutive channels (c % 4 == 0 fast path).
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        const T* __restrict__ res, int64_t ld_res, int relu, T* __restrict__ y, int64_t ld_y) {
+  const int groups = (c + 3) / 4;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * groups) return;
+  const int64_t r = t / groups;
+  const int ch = (int)(t - r * groups) * 4;
+  float v[4], rs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (kVec) {
+    Vec4<T>::load(x + r * ld_x + ch, v);
+    if (res) Vec4<T>::load(res + r * ld_res + ch, rs);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = ch + j < c ? to_f32<T>(x[r * ld_x + ch + j]) : 0.f;
+      if (res && ch + j < c) rs[j] = to_f32<T>(res[r * ld_res + ch + j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (ch + j < c) {
+      float o = fmaf(v[j], scale[ch + j], shift[ch + j]) + rs[j];
+      v[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+  }
+  if (kVec) Vec4<T>::store(y + r * ld_y + ch, v);
+  else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (ch + j < c) y[r * ld_y + ch + j] = from_f32<T>(v[j]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRedX* kRedY) bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                                     const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                                                     double* __restrict__ sums) {
+  column_reduce2(n, c, sums, [&](int64_t r, int ch, float& a, float& b) {
+    float g = to_f32<T>(dy[r * ld_dy + ch]);
+    if (relu && !(to_f32<T>(y[r * ld_y + ch]) > 0.f)) g = 0.f;
+    const float xhat = (to_f32<T>(x[r * ld_x + ch]) - mean[ch]) * invstd[ch];
+    a = g; b = g * xhat;
+  });
+}
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                            const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
+                                                            int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres, int64_t ld_dres) {
+  const int groups = (c + 3) / 4;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * groups) return;
+  const int64_t r = t / groups;
+  const int ch = (int)(t - r * groups) * 4;
+  float g[4], xv[4], yv[4] = {1.f, 1.f, 1.f, 1.f};
+  if (kVec) {
+    Vec4<T>::load(dy + r * ld_dy + ch, g);
+    Vec4<T>::load(x + r * ld_x + ch, xv);
+    if (relu) Vec4<T>::load(y + r * ld_y + ch, yv);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = ch + j < c;
+      g[j] = ok ? to_f32<T>(dy[r * ld_dy + ch + j]) : 0.f;
+      xv[j] = ok ? to_f32<T>(x[r * ld_x + ch + j]) : 0.f;
+      if (relu && ok) yv[j] = to_f32<T>(y[r * ld_y + ch + j]);
+    }
+  }
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[j] = 0.f;
+    if (ch + j < c) {
+      if (relu && !(yv[j] > 0.f)) g[j] = 0.f;
+      const float is = invstd[ch + j], gm = gamma ? gamma[ch + j] : 1.f;
+      if (training) {
+        const float xhat = (xv[j] - mean[ch + j]) * is;
+        const float sg = (float)sums[ch + j] * inv_n, sgx = (float)sums[c + ch + j] * inv_n;
+        o[j] = gm * is * (g[j] - sg - xhat * sgx);
+      } else {
+        o[j] = gm * is * g[j];
+      }
+    }
+  }
+  if (kVec) {
+    Vec4<T>::store(dx + r * ld_dx + ch, o);
+    if (dres) Vec4<T>::store(dres + r * ld_dres + ch, g);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (ch + j < c) {
+      dx[r * ld_dx + ch + j] = from_f32<T>(o[j]);
+      if (dres) dres[r * ld_dres + ch + j] = from_f32<T>(g[j]);
+    }
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int c, float* dgamma, float* dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  if (dbeta) dbeta[ch] += (float)sums[ch];
+  if (dgamma) dgamma[ch] += (float)sums[c + ch];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) relu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t numel) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < numel) y[t] = from_f32<T>(fmaxf(to_f32<T>(x[t]), 0.f));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t numel) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < numel) dx[t] = to_f32<T>(y[t]) > 0.f ? dy[t] : from_f32<T>(0.f);
+}
+
+inline unsigned reduce_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kRedY * 8), (int64_t)kNumSMs * 8)); }
+template <typename T> bool vec_ok(int c, std::initializer_list<int64_t> lds, std::initializer_list<const void*> ptrs) {
+  const int64_t a = sizeof(T) == 4 ? 16 : 8;
+  if (c % 4) return false;
+  for (int64_t ld : lds) if (ld % 4) return false;
+  for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) % a)) return false;
+  return true;
+}
+}  // namespace
+}  // namespace gcd
+
+using namespace gcd;
+
+extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c, int32_t dtype, double* stats, void* stream) {
+  GCD_REQUIRE(c >= 1 && c <= kRedX * kMaxChanIter, "gcd_bn_stats: channel count %d out of range", c);
+  if (n == 0) return GCD_OK;
+  dim3 block(kRedX, kRedY);
+  if (dtype == GCD_F32) bn_stats_kernel<float><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const float*)x, ld, n, c, stats);
+  else bn_stats_kernel<__nv_bfloat16><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, ld, n, c, stats);
+  GCD_LAUNCH_CHECK("gcd_bn_stats");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_bn_finalize(const double* stats, int64_t n, int32_t c, const float* gamma, const float* beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                                   float* scale, float* shift, void* stream) {
+  bn_finalize_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, as_stream(stream)>>>(stats, n, c, gamma, beta, eps, momentum, running_mean,
+                                                                                running_var, mean, invstd, scale, shift);
+  GCD_LAUNCH_CHECK("gcd_bn_finalize");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_bn_fold_eval(int32_t c, const float* gamma, const float* beta, const float* running_mean,
+                                    const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  bn_fold_eval_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, as_stream(stream)>>>(c, gamma, beta, running_mean, running_var, eps, scale, shift);
+  GCD_LAUNCH_CHECK("gcd_bn_fold_eval");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_bn_apply(const void* x, int64_t ld_x, int64_t n, int32_t c, const float* scale, const float* shift,
+                                const void* residual, int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream) {
+  if (n == 0) return GCD_OK;
+  cudaStream_t st = as_stream(stream);
+  const unsigned g = (unsigned)ceil_div(n * ((c + 3) / 4), 256);
+  if (dtype == GCD_F32) {
+    using T = float;
+    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
+      bn_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+    else bn_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+  } else {
+    using T = __nv_bfloat16;
+    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
+      bn_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+    else bn_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+  }
+  GCD_LAUNCH_CHECK("gcd_bn_apply");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
+                                          int64_t n, int32_t c, const float* mean, const float* invstd, int32_t relu, int32_t dtype,
+                                          double* sums, void* stream) {
+  GCD_REQUIRE(c >= 1 && c <= kRedX * kMaxChanIter, "gcd_bn_backward_reduce: channel count %d out of range", c);
+  if (n == 0) return GCD_OK;
+  dim3 block(kRedX, kRedY);
+  if (dtype == GCD_F32)
+    bn_bwd_reduce_kernel<float><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const float*)dy, ld_dy, (const float*)x, ld_x, (const float*)y, ld_y, n, c, mean, invstd, relu, sums);
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, ld_dy, (const __nv_bfloat16*)x, ld_x, (const __nv_bfloat16*)y, ld_y, n, c, mean, invstd, relu, sums);
+  GCD_LAUNCH_CHECK("gcd_bn_backward_reduce");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_bn_backward_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
+                                         int64_t n, int32_t c, const float* mean, const float* invstd, const float* gamma,
+                                         const double* sums, int32_t relu, int32_t training, void* dx, int64_t ld_dx, void* dres,
+                                         int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  if (n > 0) {
+    const unsigned g = (unsigned)ceil_div(n * ((c + 3) / 4), 256);
+    if (dtype == GCD_F32) {
+      using T = float;
+      if (vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}))
+        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+      else
+        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+    } else {
+      using T = __nv_bfloat16;
+      if (vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}))
+        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+      else
+        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+    }
+  }
+  if (dgamma || dbeta) bn_param_grad_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(sums, c, dgamma, dbeta);
+  GCD_LAUNCH_CHECK("gcd_bn_backward_apply");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_relu(const void* x, void* y, int64_t numel, int32_t dtype, void* stream) {
+  if (numel == 0) return GCD_OK;
+  const unsigned g = (unsigned)ceil_div(numel, 256);
+  if (dtype == GCD_F32) relu_kernel<float><<<g, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, numel);
+  else relu_kernel<__nv_bfloat16><<<g, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, numel);
+  GCD_LAUNCH_CHECK("gcd_relu");
+  return GCD_OK;
+}
+extern "C" int32_t gcd_relu_backward(const void* dy, const void* y, void* dx, int64_t numel, int32_t dtype, void* stream) {
+  if (numel == 0) return GCD_OK;
+  const unsigned g = (unsigned)ceil_div(numel, 256);
+  if (dtype == GCD_F32) relu_bwd_kernel<float><<<g, 256, 0, as_stream(stream)>>>((const float*)dy, (const float*)y, (float*)dx, numel);
+  else relu_bwd_kernel<__nv_bfloat16><<<g, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, numel);
+  GCD_LAUNCH_CHECK("gcd_relu_backward");
+  return GCD_OK;
+}

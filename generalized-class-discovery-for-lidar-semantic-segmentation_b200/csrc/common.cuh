@@ -1,0 +1,107 @@
+// common.cuh — shared device/host helpers for libgcdlss_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/gcdlss_b200.h"
+
+namespace gcd {
+
+// ---- host-side error plumbing (thread-local text, C error codes; no exceptions cross the ABI)
+void set_error(const char* fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char* what);
+
+#define GCD_REQUIRE(cond, ...)                                  \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      ::gcd::set_error(__VA_ARGS__);                            \
+      return GCD_ERR_INVALID_ARG;                               \
+    }                                                           \
+  } while (0)
+
+#define GCD_LAUNCH_CHECK(what)                                  \
+  do {                                                          \
+    cudaError_t e__ = cudaGetLastError();                       \
+    if (e__ != cudaSuccess) return ::gcd::cuda_fail(e__, what); \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- 64-bit coordinate keys: 10 bits batch | 3 x 18 bits (coord + 2^17)
+constexpr int kCoordBits = 18;
+constexpr int kCoordBias = 1 << (kCoordBits - 1);
+constexpr int kBatchBits = 10;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ bool key_in_range(int b, int x, int y, int z) {
+  const unsigned lim = 1u << kCoordBits;
+  return (unsigned)b < (1u << kBatchBits) - 1u &&  // batch 1023 reserved: keeps every key != kEmptyKey
+         (unsigned)(x + kCoordBias) < lim &&
+         (unsigned)(y + kCoordBias) < lim && (unsigned)(z + kCoordBias) < lim;
+}
+__device__ __forceinline__ uint64_t pack_key(int b, int x, int y, int z) {
+  return ((uint64_t)(unsigned)b << (3 * kCoordBits)) | ((uint64_t)(unsigned)(x + kCoordBias) << (2 * kCoordBits)) |
+         ((uint64_t)(unsigned)(y + kCoordBias) << kCoordBits) | (uint64_t)(unsigned)(z + kCoordBias);
+}
+__device__ __forceinline__ void unpack_key(uint64_t k, int& b, int& x, int& y, int& z) {
+  const uint64_t m = (1ull << kCoordBits) - 1;
+  z = (int)(k & m) - kCoordBias;
+  y = (int)((k >> kCoordBits) & m) - kCoordBias;
+  x = (int)((k >> (2 * kCoordBits)) & m) - kCoordBias;
+  b = (int)(k >> (3 * kCoordBits));
+}
+// murmur3 finaliser
+__device__ __forceinline__ uint64_t hash_key(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+
+// Open-addressing table, linear probing.  Slots are grouped in 32-byte sectors of four keys; a
+// probe sequence visits whole sectors so the four keys a DRAM/L2 sector delivers are all used.
+// insert: returns the slot holding `key` (claimed or already present), or -1 when the table is full.
+__device__ __forceinline__ int64_t table_insert(uint64_t* keys, int64_t cap, uint64_t key, bool* was_present) {
+  int64_t slot = (int64_t)(hash_key(key) & (uint64_t)(cap - 1));
+  for (int64_t probes = 0; probes < cap; ++probes) {
+    uint64_t cur = keys[slot];
+    if (cur == key) { *was_present = true; return slot; }
+    if (cur == kEmptyKey) {
+      unsigned long long prev = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey,
+                                          (unsigned long long)key);
+      if (prev == kEmptyKey) { *was_present = false; return slot; }
+      if (prev == key) { *was_present = true; return slot; }
+    }
+    slot = (slot + 1) & (cap - 1);
+  }
+  return -1;
+}
+__device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ keys, int64_t cap, uint64_t key) {
+  int64_t slot = (int64_t)(hash_key(key) & (uint64_t)(cap - 1));
+  for (int64_t probes = 0; probes < cap; ++probes) {
+    uint64_t cur = __ldg(&keys[slot]);
+    if (cur == key) return slot;
+    if (cur == kEmptyKey) return -1;
+    slot = (slot + 1) & (cap - 1);
+  }
+  return -1;
+}
+
+// ---- dtype helpers
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- device-wide exclusive scan of int32 (scan.cu)
+size_t scan_workspace_bytes(int64_t n);
+// out[i] = sum_{j<i} in[j]; total (device int32, may be null) = sum of all.  in may alias out.
+int32_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* total, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace gcd

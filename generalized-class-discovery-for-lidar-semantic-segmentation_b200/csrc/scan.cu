@@ -1,0 +1,106 @@
+// scan.cu — device-wide exclusive scan of int32 (three small kernels; used by the compactions
+// of the quantiser, the coarse-map builder and the pair-list builder).
+#include "common.cuh"
+
+namespace gcd {
+namespace {
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 1024
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) >= d) v += t;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one value per thread; returns exclusive prefix, writes block total.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[kScanThreads / 32];
+  __shared__ int block_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = warp_inclusive_scan(v);
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+    int si = warp_inclusive_scan(s);
+    if (lane < kScanThreads / 32) warp_sums[lane] = si - s;
+    if (lane == kScanThreads / 32 - 1) block_total = si;
+  }
+  __syncthreads();
+  int r = inc - v + warp_sums[warp];
+  *total = block_total;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                                   int64_t n, int32_t* __restrict__ tile_sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    sum += v[i];
+  }
+  int total;
+  int prefix = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = prefix;
+    prefix += v[i];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// Single block: exclusive scan of the tile sums in place, total written out.
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int32_t* __restrict__ sums, int64_t n_tiles,
+                                                                  int32_t* __restrict__ total_out) {
+  int carry = 0;
+  for (int64_t base = 0; base < n_tiles; base += kScanThreads) {
+    int64_t i = base + threadIdx.x;
+    int v = i < n_tiles ? sums[i] : 0;
+    int total;
+    int p = block_exclusive_scan(v, &total);
+    if (i < n_tiles) sums[i] = p + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int32_t* __restrict__ out, int64_t n,
+                                                                 const int32_t* __restrict__ tile_sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  const int add = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) out[base + i] += add;
+}
+}  // namespace
+
+size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)(ceil_div(n > 0 ? n : 1, kScanTile)) * sizeof(int32_t), 256); }
+
+int32_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* total, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
+  if (n <= 0) {
+    if (total) cudaMemsetAsync(total, 0, sizeof(int32_t), stream);
+    return GCD_OK;
+  }
+  if (workspace_bytes < scan_workspace_bytes(n)) {
+    set_error("exclusive_scan_i32: workspace too small");
+    return GCD_ERR_WORKSPACE;
+  }
+  int32_t* sums = static_cast<int32_t*>(workspace);
+  const int64_t n_tiles = ceil_div(n, kScanTile);
+  scan_tiles_kernel<<<(unsigned)n_tiles, kScanThreads, 0, stream>>>(in, out, n, sums);
+  scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(sums, n_tiles, total);
+  if (n_tiles > 1) scan_add_kernel<<<(unsigned)n_tiles, kScanThreads, 0, stream>>>(out, n, sums);
+  GCD_LAUNCH_CHECK("exclusive_scan_i32");
+  return GCD_OK;
+}
+}  // namespace gcd

@@ -1,0 +1,112 @@
+"""Coordinate manager: per-resolution coordinate maps, their hash tables and cached kernel maps.
+
+Plays the role of MinkowskiEngine's CoordinateManager for the layer types MinkUNet uses
+(ref models/minkunet.py:62-128): one instance is created by ``SparseTensor`` and shared by every
+tensor derived from it, so a teacher and a student that consume the same input tensor
+(ref modules/exp_merge_mean_teacher.py:2802-2805) share all maps, as they do under ME.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class CoordMap:
+    __slots__ = ("coords", "n", "table", "tensor_stride", "parent", "code")
+
+    def __init__(self, coords, table, tensor_stride):
+        self.coords, self.n, self.table, self.tensor_stride = coords, coords.shape[0], table, tensor_stride
+        self.parent = None   # [n] row of the 2x coarser map (filled when that map is created)
+        self.code = None     # [n] child offset index dx + 2dy + 4dz
+
+
+class KernelMap:
+    """A dense neighbour table plus, lazily, its per-offset pair lists.
+
+    nbr [kv, n_out] int32 feeds the output-stationary forward; ``back`` names the table and weight
+    orientation of the matching dgrad (see include/gcdlss_b200.h, gcd_conv_args)."""
+
+    def __init__(self, nbr, n_in, n_out, kv, back_nbr_fn, back_mirror):
+        self.nbr, self.n_in, self.n_out, self.kv = nbr, n_in, n_out, kv
+        self._back_nbr_fn, self.back_mirror = back_nbr_fn, back_mirror
+        self._pairs = None
+        self._back = None
+
+    @property
+    def pairs(self):
+        if self._pairs is None:
+            self._pairs = ops.pairs_from_table(self.nbr) if self.nbr is not None else None
+        return self._pairs
+
+    @property
+    def back_nbr(self):
+        if self._back is None and self._back_nbr_fn is not None:
+            self._back = self._back_nbr_fn()
+        return self._back
+
+    def num_pairs(self) -> int:
+        """Exact pair count (one device read; used for FLOP accounting only)."""
+        if self.nbr is None:
+            return self.n_out
+        return int(self.pairs[2][-1].item())
+
+
+class CoordinateManager:
+    def __init__(self, coords: torch.Tensor):
+        if coords.dim() != 2 or coords.shape[1] != 4:
+            raise ValueError("coordinates must be [N, 4] (batch, x, y, z)")
+        coords = coords.to(torch.int32).contiguous()
+        self.device = coords.device
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.maps = {1: CoordMap(coords, ops.hash_build(coords, self.status), 1)}
+        self._kmaps = {}
+
+    # -- coordinate maps -------------------------------------------------------------------
+    def check(self):
+        """Raise if any device-side build reported a key-range / duplicate / overflow condition."""
+        ops._status_check(self.status, "SparseTensor coordinates")
+
+    def get_map(self, tensor_stride: int) -> CoordMap:
+        if tensor_stride not in self.maps:
+            if tensor_stride < 2 or tensor_stride % 2:
+                raise KeyError(f"no coordinate map at tensor stride {tensor_stride}")
+            fine = self.get_map(tensor_stride // 2)
+            coarse, parent, code, table = ops.coords_stride2(fine.coords, fine.tensor_stride, self.status)
+            self.check()  # the call above already synchronised to learn the coarse voxel count
+            fine.parent, fine.code = parent, code
+            self.maps[tensor_stride] = CoordMap(coarse, table, tensor_stride)
+        return self.maps[tensor_stride]
+
+    # -- kernel maps -----------------------------------------------------------------------
+    def kernel_map(self, ts_in: int, kernel_size: int, stride: int, transposed: bool) -> KernelMap:
+        key = (ts_in, kernel_size, stride, transposed)
+        km = self._kmaps.get(key)
+        if km is not None:
+            return km
+        if kernel_size == 1 and stride == 1:
+            m = self.get_map(ts_in)
+            km = KernelMap(None, m.n, m.n, 1, None, False)
+        elif stride == 1 and kernel_size in (3, 5) and not transposed:
+            m = self.get_map(ts_in)
+            nbr = ops.kmap_subm(m.coords, m.table, kernel_size, ts_in)
+            # stride-1 symmetric kernel: the transposed map is the same table with mirrored offsets
+            km = KernelMap(nbr, m.n, m.n, kernel_size ** 3, lambda: nbr, True)
+        elif stride == 2 and kernel_size == 2 and not transposed:
+            fine = self.get_map(ts_in)
+            coarse = self.get_map(ts_in * 2)
+            nbr = ops.kmap_down2(fine.parent, fine.code, coarse.n)
+            km = KernelMap(nbr, fine.n, coarse.n, 8, lambda: self.kernel_map(ts_in * 2, 2, 2, True).nbr, False)
+        elif stride == 2 and kernel_size == 2 and transposed:
+            if ts_in % 2 or ts_in // 2 not in self.maps:
+                raise RuntimeError("transposed convolution needs the finer coordinate map to exist already "
+                                   "(MinkUNet decoders only upsample onto encoder maps)")
+            fine = self.get_map(ts_in // 2)
+            coarse = self.get_map(ts_in)
+            nbr = ops.kmap_up2(fine.parent, fine.code)
+            km = KernelMap(nbr, coarse.n, fine.n, 8, lambda: self.kernel_map(ts_in // 2, 2, 2, False).nbr, False)
+        else:
+            raise NotImplementedError(f"kernel_size={kernel_size}, stride={stride}, transposed={transposed} is not on the "
+                                      "MinkUNet path (supported: 1/1, 3/1, 5/1, 2/2 and transposed 2/2)")
+        self._kmaps[key] = km
+        return km

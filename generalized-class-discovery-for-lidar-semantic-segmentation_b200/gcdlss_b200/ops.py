@@ -1,0 +1,366 @@
+"""Tensor-level wrappers over the C ABI: every function takes CUDA torch tensors (used only as
+device memory + the current stream) and enqueues hand-written sm_100a kernels.  Nothing here
+computes with torch ops."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import BF16, F32, MATH_BF16_TC, MATH_FP32_SIMT, ConvArgs, WgradArgs, call, lib
+
+# Count of kernel-launching C-ABI calls, for bench.py's "gpu_launches" claim.
+launch_counter = {"calls": 0}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported feature dtype {t.dtype}")
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gcdlss_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _count(n=1):
+    launch_counter["calls"] += n
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.dim() == 2 and t.stride(1) == 1) or t.numel() == 0 else t.contiguous()
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+# ------------------------------------------------------------------------------------ quantise
+def quantize(points: torch.Tensor, q: float, dims: int, round_mode: int) -> torch.Tensor:
+    """int32 [n, dims] = round_mode(points[:, :dims] / q); points fp32 or fp64, row-major."""
+    _require_cuda(points)
+    points = _rowmajor(points)
+    n = points.shape[0]
+    out = torch.empty((n, dims), dtype=torch.int32, device=points.device)
+    if points.dtype == torch.float32:
+        call("gcd_quantize_f32", _ptr(points), _ld(points), n, dims, float(q), round_mode, _ptr(out), _stream())
+    elif points.dtype == torch.float64:
+        call("gcd_quantize_f64", _ptr(points), _ld(points), n, dims, float(q), round_mode, _ptr(out), _stream())
+    else:
+        raise TypeError("points must be float32 or float64")
+    _count()
+    return out
+
+
+def shift_to_min(coords: torch.Tensor) -> torch.Tensor:
+    """coords -= coords.min(0), in place (ref models/voxelizer.py:276)."""
+    n, dims = coords.shape
+    mins = torch.full((4,), 2**31 - 1, dtype=torch.int32, device=coords.device)
+    call("gcd_colmin_i32", _ptr(coords), n, dims, _ptr(mins), _stream())
+    call("gcd_sub_cols_i32", _ptr(coords), n, dims, _ptr(mins), _stream())
+    _count(2)
+    return coords
+
+
+class HashTable:
+    """Device memory of one open-addressing table (keys uint64 as int64 storage, vals int32)."""
+
+    def __init__(self, n: int, device):
+        self.cap = int(lib().gcd_hash_capacity(n))
+        self.keys = torch.empty(self.cap, dtype=torch.int64, device=device)
+        self.vals = torch.empty(self.cap, dtype=torch.int32, device=device)
+
+
+def _status_check(status: torch.Tensor, what: str):
+    s = int(status.item())
+    if s:
+        msgs = []
+        if s & _cabi.DEV_KEY_RANGE:
+            msgs.append("a coordinate does not fit the 64-bit key (|coord| < 2^17, 0 <= batch < 1023)")
+        if s & _cabi.DEV_DUPLICATE:
+            msgs.append("duplicate coordinates (quantise the input first)")
+        if s & _cabi.DEV_TABLE_FULL:
+            msgs.append("hash table full")
+        raise RuntimeError(f"{what}: " + "; ".join(msgs))
+
+
+def unique_rows(icoords: torch.Tensor, order: int = 0):
+    """Unique rows of int32 [n, 3|4].  Returns (unique_idx [M] int64, inverse [n] int64, table)."""
+    _require_cuda(icoords)
+    icoords = icoords.contiguous()
+    n, dims = icoords.shape
+    dev = icoords.device
+    table = HashTable(n, dev)
+    ws_bytes = int(lib().gcd_unique_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    unique_idx = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    inverse = torch.empty(n, dtype=torch.int64, device=dev)
+    meta = torch.zeros(2, dtype=torch.int32, device=dev)  # [m, status]
+    call("gcd_unique_rows", _ptr(icoords), n, dims, order, _ptr(table.keys), _ptr(table.vals), table.cap, _ptr(unique_idx),
+         _ptr(inverse), _ptr(meta[0:1]), _ptr(ws), ws_bytes, _ptr(meta[1:2]), _stream())
+    _count(7 if order == 0 else 40)
+    m, status = meta.tolist()
+    if status:
+        _status_check(meta[1:2], "sparse_quantize")
+    return unique_idx[:m], inverse, table
+
+
+# ------------------------------------------------------------------------------------ coordinate maps
+def hash_build(coords: torch.Tensor, status: torch.Tensor) -> HashTable:
+    n = coords.shape[0]
+    table = HashTable(n, coords.device)
+    call("gcd_hash_build", _ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.cap, _ptr(status), _stream())
+    _count(2)
+    return table
+
+
+def coords_stride2(coords: torch.Tensor, ts: int, status: torch.Tensor):
+    """Returns (coarse coords [M,4], parent [n], code [n], coarse table)."""
+    n = coords.shape[0]
+    dev = coords.device
+    table = HashTable(n, dev)
+    ws_bytes = int(lib().gcd_stride2_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    coarse = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    parent = torch.empty(n, dtype=torch.int32, device=dev)
+    code = torch.empty(n, dtype=torch.int32, device=dev)
+    m_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("gcd_coords_stride2", _ptr(coords), n, ts, _ptr(table.keys), _ptr(table.vals), table.cap, _ptr(coarse), _ptr(parent),
+         _ptr(code), _ptr(m_dev), _ptr(ws), ws_bytes, _ptr(status), _stream())
+    _count(8)
+    m = int(m_dev.item())
+    return coarse[:m], parent, code, table
+
+
+def kmap_subm(coords: torch.Tensor, table: HashTable, kernel_size: int, ts: int) -> torch.Tensor:
+    n = coords.shape[0]
+    kv = kernel_size ** 3
+    nbr = torch.empty((kv, n), dtype=torch.int32, device=coords.device)
+    call("gcd_kmap_subm", _ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.cap, kernel_size, ts, _ptr(nbr), _stream())
+    _count()
+    return nbr
+
+
+def kmap_down2(parent, code, n_coarse: int) -> torch.Tensor:
+    nbr = torch.empty((8, n_coarse), dtype=torch.int32, device=parent.device)
+    call("gcd_kmap_down2", _ptr(parent), _ptr(code), parent.shape[0], n_coarse, _ptr(nbr), _stream())
+    _count(2)
+    return nbr
+
+
+def kmap_up2(parent, code) -> torch.Tensor:
+    nbr = torch.empty((8, parent.shape[0]), dtype=torch.int32, device=parent.device)
+    call("gcd_kmap_up2", _ptr(parent), _ptr(code), parent.shape[0], _ptr(nbr), _stream())
+    _count()
+    return nbr
+
+
+def pairs_from_table(nbr: torch.Tensor):
+    """(pair_in, pair_out, pair_off) of a [kv, n_out] table; arrays sized for the worst case."""
+    kv, n_out = nbr.shape
+    dev = nbr.device
+    cap = max(kv * n_out, 1)
+    pair_in = torch.empty(cap, dtype=torch.int32, device=dev)
+    pair_out = torch.empty(cap, dtype=torch.int32, device=dev)
+    pair_off = torch.empty(kv + 1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib().gcd_pairs_workspace_bytes(n_out, kv))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("gcd_pairs_from_table", _ptr(nbr), n_out, kv, _ptr(pair_in), _ptr(pair_out), _ptr(pair_off), _ptr(ws), ws_bytes, _stream())
+    _count(5)
+    return pair_in, pair_out, pair_off
+
+
+# ------------------------------------------------------------------------------------ convolution
+def tc_supported(c_in: int, c_out: int, kv: int) -> bool:
+    return bool(lib().gcd_conv_tc_supported(c_in, c_out, kv))
+
+
+def pack_weights(w: torch.Tensor, transpose: bool, mirror: bool) -> torch.Tensor:
+    """bf16 operand image of fp32 kernel [kv, c_in, c_out] for the tcgen05 path."""
+    kv, c_in, c_out = w.shape
+    nbytes = int(lib().gcd_conv_packed_weight_bytes(kv, c_in, c_out))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    call("gcd_conv_pack_weights", _ptr(w), kv, c_in, c_out, int(transpose), int(mirror), _ptr(packed), _stream())
+    _count()
+    return packed
+
+
+def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=MATH_FP32_SIMT,
+                 w_packed=None, stats=None):
+    """out[o] = sum_k inp[nbr[k, o]] @ B_k, B_k = w3[k] (or w3[wsel(k)]^T when transpose_w).
+
+    inp [n_in, c_in'] row-major; nbr [kv, n_out] int32 or None (identity); w3 fp32 [kv, c_in, c_out].
+    """
+    _require_cuda(inp, w3)
+    inp = _rowmajor(inp)
+    kv, c_in, c_out = w3.shape
+    k_dim, n_dim = (c_out, c_in) if transpose_w else (c_in, c_out)
+    if inp.shape[1] != k_dim:
+        raise ValueError(f"feature width {inp.shape[1]} does not match the kernel ({k_dim})")
+    out_dtype = out_dtype or inp.dtype
+    out = torch.empty((n_out, n_dim), dtype=out_dtype, device=inp.device)
+    a = ConvArgs()
+    a.inp, a.ld_in, a.n_in = inp.data_ptr(), _ld(inp), inp.shape[0]
+    a.nbr = nbr.data_ptr() if nbr is not None else None
+    a.kv, a.n_out, a.c_in, a.c_out = kv, n_out, k_dim, n_dim
+    a.w = w3.data_ptr()
+    a.w_packed = w_packed.data_ptr() if w_packed is not None else None
+    if transpose_w:
+        a.w_stride_k, a.w_stride_c, a.w_stride_n = c_in * c_out, 1, c_out
+    else:
+        a.w_stride_k, a.w_stride_c, a.w_stride_n = c_in * c_out, c_out, 1
+    a.mirror = int(mirror)
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.out, a.ld_out = out.data_ptr(), n_dim
+    a.in_dtype, a.out_dtype = _dtype_code(inp), _dtype_code(out)
+    a.stats = stats.data_ptr() if stats is not None else None
+    a.math_mode = math_mode
+    call("gcd_conv_forward", C.byref(a), _stream())
+    _count()
+    return out
+
+
+def conv_wgrad(inp, gout, pairs, kv: int, dw: torch.Tensor, dbias=None, math_mode=MATH_FP32_SIMT):
+    """dw[k] += inp[pair_in]^T gout[pair_out] (accumulating); pairs = (pair_in, pair_out, pair_off) or None (identity)."""
+    _require_cuda(inp, gout, dw)
+    inp, gout = _rowmajor(inp), _rowmajor(gout)
+    a = WgradArgs()
+    a.inp, a.ld_in = inp.data_ptr(), _ld(inp)
+    a.gout, a.ld_gout = gout.data_ptr(), _ld(gout)
+    if pairs is not None:
+        a.pair_in, a.pair_out, a.pair_off = pairs[0].data_ptr(), pairs[1].data_ptr(), pairs[2].data_ptr()
+        a.n_pairs = pairs[0].shape[0]
+    else:
+        a.pair_in = a.pair_out = a.pair_off = None
+        a.n_pairs = inp.shape[0]
+    a.kv, a.c_in, a.c_out = kv, inp.shape[1], gout.shape[1]
+    a.dw = dw.data_ptr()
+    a.dbias = dbias.data_ptr() if dbias is not None else None
+    a.n_out = gout.shape[0]
+    a.in_dtype, a.gout_dtype = _dtype_code(inp), _dtype_code(gout)
+    a.math_mode = math_mode
+    call("gcd_conv_wgrad", C.byref(a), _stream())
+    _count(2 if dbias is not None else 1)
+
+
+def im2col(inp, nbr, ld_out: int, out_dtype) -> torch.Tensor:
+    inp = _rowmajor(inp)
+    kv, n_out = nbr.shape
+    out = torch.empty((n_out, ld_out), dtype=out_dtype, device=inp.device)
+    call("gcd_im2col", _ptr(inp), _ld(inp), inp.shape[1], _ptr(nbr), kv, n_out, _ptr(out), ld_out, _dtype_code(inp), _dtype_code(out), _stream())
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------ batch norm
+def bn_forward(x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool, residual=None):
+    """Returns (y, mean, invstd); mean/invstd are the statistics used (batch or running)."""
+    _require_cuda(x)
+    x = _rowmajor(x)
+    n, c = x.shape
+    dev = x.device
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    scale = torch.empty(c, dtype=torch.float32, device=dev)
+    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    st = _stream()
+    if training:
+        stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+        call("gcd_bn_stats", _ptr(x), _ld(x), n, c, _dtype_code(x), _ptr(stats), st)
+        call("gcd_bn_finalize", _ptr(stats), n, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum), _ptr(running_mean),
+             _ptr(running_var), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), st)
+        _count(2)
+    else:
+        call("gcd_bn_fold_eval", c, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), st)
+        mean = running_mean
+        invstd = torch.rsqrt(running_var + eps)
+        _count()
+    y = torch.empty_like(x)
+    if residual is not None:
+        residual = _rowmajor(residual)
+    call("gcd_bn_apply", _ptr(x), _ld(x), n, c, _ptr(scale), _ptr(shift), _ptr(residual), _ld(residual) if residual is not None else 0,
+         int(relu), _ptr(y), _ld(y), _dtype_code(x), st)
+    _count()
+    return y, mean, invstd
+
+
+def bn_backward(dy, x, y, mean, invstd, gamma, relu: bool, training: bool, need_dres: bool):
+    """Returns (dx, dres or None, dgamma, dbeta)."""
+    dy = _rowmajor(dy)
+    n, c = x.shape
+    dev = x.device
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+    st = _stream()
+    call("gcd_bn_backward_reduce", _ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(y), _ld(y) if y is not None else 0, n, c, _ptr(mean), _ptr(invstd),
+         int(relu), _dtype_code(x), _ptr(sums), st)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if need_dres else None
+    dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(c, dtype=torch.float32, device=dev)
+    call("gcd_bn_backward_apply", _ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(y), _ld(y) if y is not None else 0, n, c, _ptr(mean), _ptr(invstd),
+         _ptr(gamma), _ptr(sums), int(relu), int(training), _ptr(dx), _ld(dx), _ptr(dres), _ld(dres) if dres is not None else 0,
+         _ptr(dgamma), _ptr(dbeta), _dtype_code(x), st)
+    _count(3)
+    return dx, dres, dgamma, dbeta
+
+
+def relu(x):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    call("gcd_relu", _ptr(x), _ptr(y), x.numel(), _dtype_code(x), _stream())
+    _count()
+    return y
+
+
+def relu_backward(dy, y):
+    dy = dy.contiguous()
+    dx = torch.empty_like(dy)
+    call("gcd_relu_backward", _ptr(dy), _ptr(y), _ptr(dx), dy.numel(), _dtype_code(dy), _stream())
+    _count()
+    return dx
+
+
+# ------------------------------------------------------------------------------------ voxel <-> point
+def rows_gather(x, idx):
+    _require_cuda(x, idx)
+    x = _rowmajor(x.float())
+    idx = idx.contiguous()
+    out = torch.empty((idx.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    call("gcd_rows_gather", _ptr(x), _ld(x), _ptr(idx), idx.shape[0], x.shape[1], _ptr(out), x.shape[1], _stream())
+    _count()
+    return out
+
+
+def csr_build(idx, n_segments: int):
+    """(seg_off [n_segments+1] int32, order [n_points] int32): points grouped by segment, ascending."""
+    idx = idx.contiguous()
+    n = idx.shape[0]
+    dev = idx.device
+    seg_off = torch.empty(n_segments + 1, dtype=torch.int32, device=dev)
+    order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib().gcd_csr_workspace_bytes(n, n_segments))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("gcd_csr_build", _ptr(idx), n, n_segments, _ptr(seg_off), _ptr(order), _ptr(ws), ws_bytes, _stream())
+    _count(12)
+    return seg_off, order[:n]
+
+
+def segment_reduce(x, seg_off, order, n_segments: int, mode: int):
+    x = _rowmajor(x.float())
+    out = torch.empty((n_segments, x.shape[1]), dtype=torch.float32, device=x.device)
+    call("gcd_segment_reduce", _ptr(x), _ld(x), _ptr(seg_off), _ptr(order), n_segments, x.shape[1], mode, _ptr(out), x.shape[1], _stream())
+    _count()
+    return out

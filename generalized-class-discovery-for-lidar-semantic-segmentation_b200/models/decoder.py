@@ -1,0 +1,82 @@
+"""Drop-in for the reference ``models/decoder.py``: segmentation decode heads of the mmdet3d-style
+path (ref models/decoder.py:16-426) without the mmengine/mmdet3d registries.  ``MinkUNetHead``
+classifies voxel features with ``nn.Linear`` and devoxelises the logits back to points through the
+gather kernel (ref :416-424); ``Cylinder3DHead`` (3x3x3 SubMConv logits) is SURVEY 8(f) rank 4.
+"""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from gcdlss_b200.functional import devoxelize
+
+
+class Base3DDecodeHead(nn.Module):
+    def __init__(self, channels: int, num_classes: int, dropout_ratio: float = 0.5, conv_cfg=None, norm_cfg=None, act_cfg=None,
+                 loss_decode=None, conv_seg_kernel_size: int = 1, ignore_index: int = 255, init_cfg=None) -> None:
+        super().__init__()
+        self.channels = channels
+        self.num_classes = num_classes
+        self.dropout_ratio = dropout_ratio
+        self.ignore_index = ignore_index
+        cfg = dict(loss_decode or {})
+        self.loss_weight = float(cfg.get('loss_weight', 1.0))
+        self.class_weight = cfg.get('class_weight', None)
+        self.conv_seg = self.build_conv_seg(channels=channels, num_classes=num_classes, kernel_size=conv_seg_kernel_size)
+        self.dropout = nn.Dropout(dropout_ratio) if dropout_ratio > 0 else None
+
+    def build_conv_seg(self, channels: int, num_classes: int, kernel_size: int) -> nn.Module:
+        return nn.Conv1d(channels, num_classes, kernel_size=kernel_size)
+
+    def loss_decode(self, seg_logit: Tensor, seg_label: Tensor) -> Tensor:
+        w = seg_logit.new_tensor(self.class_weight) if self.class_weight is not None else None
+        return self.loss_weight * F.cross_entropy(seg_logit, seg_label.long(), weight=w, ignore_index=self.ignore_index)
+
+    def cls_seg(self, feat: Tensor) -> Tensor:
+        if self.dropout is not None:
+            feat = self.dropout(feat)
+        return self.conv_seg(feat)
+
+    def loss(self, inputs: dict, batch_data_samples, train_cfg=None) -> dict:
+        return self.loss_by_feat(self.forward(inputs), batch_data_samples)
+
+    def predict(self, inputs: dict, batch_input_metas: List[dict], test_cfg=None) -> Tensor:
+        return self.forward(inputs)
+
+
+class MinkUNetHead(Base3DDecodeHead):
+    """ref models/decoder.py:328-426."""
+
+    def __init__(self, batch_first: bool = True, **kwargs) -> None:
+        super().__init__(**kwargs)
+        self.batch_first = batch_first
+
+    def build_conv_seg(self, channels: int, num_classes: int, kernel_size: int) -> nn.Module:
+        return nn.Linear(channels, num_classes)
+
+    def forward(self, voxel_dict: dict) -> dict:
+        voxel_dict['logits'] = self.cls_seg(voxel_dict['voxel_feats'])
+        return voxel_dict
+
+    def loss_by_feat(self, voxel_dict: dict, batch_data_samples) -> dict:
+        # labels of the voxels: the label of each voxel's representative point (ref :368-379)
+        labels = [s.gt_pts_seg.pts_semantic_mask[inds] for s, inds in zip(batch_data_samples, voxel_dict['voxel_inds'])]
+        return {'loss_ce': self.loss_decode(voxel_dict['logits'], torch.cat(labels))}
+
+    def predict(self, voxel_dict: dict, batch_data_samples=None) -> List[Tensor]:
+        """Per-scan point logits: logits of the scan's voxels gathered through point2voxel_map (ref :381-426)."""
+        voxel_dict = self.forward(voxel_dict)
+        logits, coors = voxel_dict['logits'], voxel_dict['coors']
+        bcol = coors[:, 0] if self.batch_first else coors[:, -1]
+        out = []
+        for b, p2v in enumerate(voxel_dict['point2voxel_maps']):
+            scan_logits = logits[bcol == b]
+            out.append(devoxelize(scan_logits, p2v.long()))
+        return out
+
+
+class Cylinder3DHead(Base3DDecodeHead):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("Cylinder3DHead (3x3x3 SubMConv3d logits on the Cylinder3D path) is SURVEY 8(f) rank 4 (next)")

@@ -1,0 +1,247 @@
+/*
+ * gcdlss_b200.h — C ABI of libgcdlss_sm100a.so
+ *
+ * The sm_100a (B200) implementation of the one data-parallel hot path of GCDLSS:
+ * point->voxel quantisation, coordinate / kernel-map construction, sparse convolution
+ * (forward, dgrad, wgrad), batch-norm(+ReLU,+residual) and voxel<->point gathers/reductions.
+ *
+ * What each group replaces in the reference (the reference has no FFI of its own: its hot
+ * path calls MinkowskiEngine / mmcv native extensions from Python, so "the entry points the
+ * reference's FFI for this path would bind" are the calls those Python sites make):
+ *
+ *   gcd_quantize_*, gcd_unique_*   ME.utils.sparse_quantize             utils/dataset_remission.py:868-873,
+ *                                                                      modules/exp_merge_mean_teacher.py:2856-2861
+ *                                  Voxelizer.voxelize / ravel_hash /    models/voxelizer.py:271-302, 312-360
+ *                                  sparse_quantize (np.unique flavour)
+ *   gcd_hash_build                 ME.SparseTensor(coordinates=...)     modules/exp.py:259, exp_merge_mean_teacher.py:2802
+ *   gcd_coords_stride2,            ME CoordinateManager stride / kernel models/minkunet.py:62-128 (every MinkowskiConvolution /
+ *   gcd_kmap_*                     map generation                       MinkowskiConvolutionTranspose call)
+ *   gcd_conv_*                     MinkowskiConvolution(Transpose)      models/minkunet.py:140-214, resnet_block BasicBlock
+ *                                  forward / backward
+ *   gcd_bn_*                       ME.MinkowskiBatchNorm + MinkowskiReLU models/minkunet.py:65,130 (+ residual add of BasicBlock)
+ *   gcd_rows_gather, gcd_csr_*,    voxel->point devoxelisation gather   models/decoder.py:416-424,
+ *   gcd_segment_*                  and its segmented-sum backward;      modules/exp_merge_mean_teacher.py:2845-2846;
+ *                                  point->voxel mean/max reduce         models/encoder.py:121-164 (mmcv DynamicScatter)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++ or torch types cross the boundary.
+ *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all
+ *     memory, including workspaces and hash tables; the library never allocates, frees or keeps
+ *     a pointer past the call.  All work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 on success, a negative gcd_status otherwise; gcd_last_error_string()
+ *     gives the text for the calling thread.  Conditions only detectable on the device (key
+ *     range overflow, duplicate coordinates, hash table full) are reported through the
+ *     caller-provided `status` word (int32, device) that the caller must zero beforehand and
+ *     reads back when it next synchronises; bits are gcd_dev_status.
+ *   - Row-major matrices with an explicit leading dimension where one is given.
+ *   - Voxel coordinates are int32 (b, x, y, z).  Hash keys pack them into 64 bits:
+ *     10 bits batch | 3 x 18 bits (coordinate + 2^17); anything outside sets GCD_DEV_KEY_RANGE.
+ *   - Kernel maps are dense neighbour tables stored column-major: nbr[k * n_out + o] is the
+ *     input row feeding output row o through kernel offset k, or -1.  Offset order: x fastest,
+ *     odd K centred, even K one-sided (MinkowskiEngine convention).
+ */
+#ifndef GCDLSS_B200_H_
+#define GCDLSS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GCD_OK = 0,
+  GCD_ERR_INVALID_ARG = -1,
+  GCD_ERR_CUDA = -2,
+  GCD_ERR_UNSUPPORTED = -3,
+  GCD_ERR_WORKSPACE = -4
+} gcd_status;
+
+typedef enum {
+  GCD_DEV_KEY_RANGE = 1,  /* a coordinate does not fit the 64-bit key */
+  GCD_DEV_DUPLICATE = 2,  /* gcd_hash_build saw the same coordinate twice */
+  GCD_DEV_TABLE_FULL = 4  /* probing wrapped around the whole table */
+} gcd_dev_status;
+
+typedef enum { GCD_ROUND_FLOOR = 0, GCD_ROUND_HALF_EVEN = 1 } gcd_round_mode;
+typedef enum { GCD_F32 = 0, GCD_BF16 = 1 } gcd_dtype;
+typedef enum { GCD_MATH_FP32_SIMT = 0, GCD_MATH_BF16_TCGEN05 = 1 } gcd_math_mode;
+
+const char* gcd_last_error_string(void);
+int32_t gcd_abi_version(void);
+/* 1 when the library was built with the tcgen05 kernels (always, for sm_100a). */
+int32_t gcd_has_tcgen05(void);
+
+/* ------------------------------------------------------------------ quantisation -------- */
+/* out[i, d] = (int32) round_mode( pts[i*ld + d] / q ), d < dims (dims = 3 or 4).  The division
+ * is an IEEE division in the input precision (never a multiply by a reciprocal). */
+int32_t gcd_quantize_f32(const float* pts, int64_t ld, int64_t n, int32_t dims, float q,
+                         int32_t round_mode, int32_t* out, void* stream);
+int32_t gcd_quantize_f64(const double* pts, int64_t ld, int64_t n, int32_t dims, double q,
+                         int32_t round_mode, int32_t* out, void* stream);
+/* Column-wise minimum of an int32 [n, dims] matrix (dims <= 4); mins must be pre-filled with
+ * INT32_MAX.  Used for the `res_coors -= res_coors.min(0)` shift of models/voxelizer.py:276. */
+int32_t gcd_colmin_i32(const int32_t* coords, int64_t n, int32_t dims, int32_t* mins, void* stream);
+int32_t gcd_sub_cols_i32(int32_t* coords, int64_t n, int32_t dims, const int32_t* mins, void* stream);
+
+/* Hash table capacity (slots, a power of two >= 2n) and workspace sizes. */
+int64_t gcd_hash_capacity(int64_t n);
+size_t gcd_unique_workspace_bytes(int64_t n);
+
+/* Unique rows of an int32 [n, dims] matrix (dims 3: (x,y,z), batch taken as 0; dims 4: (b,x,y,z)).
+ * order = 0: first-occurrence order (ME.utils.sparse_quantize): unique_idx ascending.
+ * order = 1: ascending (b,x,y,z) key order (np.unique on ravel_hash, models/voxelizer.py:334-360);
+ *            unique_idx[j] = first point of the j-th smallest voxel.
+ * Outputs: unique_idx [<= n] int64, inverse [n] int64, m_out (device int32) = number of voxels,
+ * and the table (keys/vals, `cap` slots) mapping voxel key -> voxel index on return. */
+int32_t gcd_unique_rows(const int32_t* coords, int64_t n, int32_t dims, int32_t order,
+                        uint64_t* table_keys, int32_t* table_vals, int64_t cap,
+                        int64_t* unique_idx, int64_t* inverse, int32_t* m_out,
+                        void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------ coordinate maps ----- */
+/* Insert n unique (b,x,y,z) rows; table maps key -> row index. */
+int32_t gcd_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals,
+                       int64_t cap, int32_t* status, void* stream);
+
+size_t gcd_stride2_workspace_bytes(int64_t n);
+/* Coarse map of a stride-2 convolution at tensor stride ts (output stride 2 ts):
+ * coarse[parent[f]] = floor(coords[f] / 2ts) * 2ts, coarse voxels numbered in first-occurrence
+ * order of their children; code[f] = dx + 2 dy + 4 dz, d = (c - coarse)/ts.
+ * The coarse table (cap_coarse slots) maps coarse key -> coarse row on return. */
+int32_t gcd_coords_stride2(const int32_t* coords, int64_t n, int32_t ts,
+                           uint64_t* coarse_keys, int32_t* coarse_vals, int64_t cap_coarse,
+                           int32_t* coarse_coords, int32_t* parent, int32_t* code, int32_t* m_out,
+                           void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* Stride-1 kernel map for kernel_size 3 or 5 at tensor stride ts: nbr [K^3][n] column-major. */
+int32_t gcd_kmap_subm(const int32_t* coords, int64_t n, const uint64_t* table_keys,
+                      const int32_t* table_vals, int64_t cap, int32_t kernel_size, int32_t ts,
+                      int32_t* nbr, void* stream);
+/* Stride-2 K=2 maps from parent/code: down: nbr [8][n_coarse] (child rows);
+ * up (transposed conv): nbr [8][n_fine] with the single entry nbr[code[f]][f] = parent[f]. */
+int32_t gcd_kmap_down2(const int32_t* parent, const int32_t* code, int64_t n_fine, int64_t n_coarse,
+                       int32_t* nbr, void* stream);
+int32_t gcd_kmap_up2(const int32_t* parent, const int32_t* code, int64_t n_fine, int32_t* nbr, void* stream);
+
+size_t gcd_pairs_workspace_bytes(int64_t n_out, int32_t kv);
+/* Per-offset pair lists of a table: pairs of offset k are [pair_off[k], pair_off[k+1]), sorted by
+ * output row.  pair_in / pair_out hold up to n_out*kv entries; pair_off is int32 [kv+1] (device). */
+int32_t gcd_pairs_from_table(const int32_t* nbr, int64_t n_out, int32_t kv, int32_t* pair_in,
+                             int32_t* pair_out, int32_t* pair_off, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ convolution --------- */
+/* Weight operand description shared by forward and dgrad:
+ *   B_k[c, j] = w[wsel(k) * w_stride_k + c * w_stride_c + j * w_stride_n],  wsel(k) = mirror ? kv-1-k : k
+ * forward:  c over Cin, j over Cout of kernel [kv, Cin, Cout]:  strides (Cin*Cout, Cout, 1), mirror 0
+ * dgrad of a stride-1 conv: same table, mirror 1, strides (Cin*Cout, 1, Cout) (i.e. W^T)
+ * dgrad of down / up convs: the opposite table (up / down), mirror 0, transposed strides. */
+typedef struct {
+  const void* in;        /* [n_in, c_in] features (dtype in_dtype), leading dimension ld_in */
+  int64_t ld_in;
+  int64_t n_in;
+  const int32_t* nbr;    /* [kv][n_out] table, or NULL = identity (kv must be 1, n_in == n_out) */
+  int32_t kv;
+  int64_t n_out;
+  int32_t c_in;
+  int32_t c_out;
+  const float* w;        /* fp32 master weights (SIMT path) */
+  const void* w_packed;  /* bf16 operand images made by gcd_conv_pack_weights (tcgen05 path) */
+  int64_t w_stride_k, w_stride_c, w_stride_n;
+  int32_t mirror;
+  const float* bias;     /* [c_out] or NULL */
+  void* out;             /* [n_out, c_out] (dtype out_dtype), leading dimension ld_out */
+  int64_t ld_out;
+  int32_t in_dtype;      /* gcd_dtype */
+  int32_t out_dtype;     /* gcd_dtype */
+  double* stats;         /* optional [2*c_out] fp64: per-channel sum and sum of squares of the
+                            fp32 result, accumulated atomically (caller zeroes), or NULL */
+  int32_t math_mode;     /* gcd_math_mode */
+} gcd_conv_args;
+
+int32_t gcd_conv_forward(const gcd_conv_args* args, void* stream);
+
+/* bf16 operand images for the tcgen05 path.  transpose = 0: forward operand of kernel
+ * [kv, c_in, c_out]; transpose = 1: dgrad operand (W[k]^T, offsets optionally mirrored). */
+size_t gcd_conv_packed_weight_bytes(int32_t kv, int32_t c_in, int32_t c_out);
+int32_t gcd_conv_pack_weights(const float* w, int32_t kv, int32_t c_in, int32_t c_out,
+                              int32_t transpose, int32_t mirror, void* packed, void* stream);
+
+/* dW[k] += in[pair_in]^T · gout[pair_out] over the pairs of each offset; dw is fp32 [kv, c_in, c_out]
+ * and is ACCUMULATED into (caller zeroes).  pair_in == NULL means identity (1x1 conv, kv == 1,
+ * n_pairs rows). */
+typedef struct {
+  const void* in;  int64_t ld_in;       /* [n_in, c_in] */
+  const void* gout; int64_t ld_gout;    /* [n_out, c_out] */
+  const int32_t* pair_in; const int32_t* pair_out; const int32_t* pair_off; /* device */
+  int64_t n_pairs;                      /* identity: number of rows; pair lists: an upper bound of the
+                                           total pair count (capacity of pair_in), the exact per-offset
+                                           counts are read from pair_off on the device */
+  int32_t kv, c_in, c_out;
+  float* dw;
+  float* dbias;                         /* optional [c_out]: += column sums of gout (caller zeroes) */
+  int64_t n_out;                        /* rows of gout (for dbias) */
+  int32_t in_dtype, gout_dtype, math_mode;
+} gcd_wgrad_args;
+
+int32_t gcd_conv_wgrad(const gcd_wgrad_args* args, void* stream);
+
+/* 1 when (c_in, c_out, kv) can run on the tcgen05 path (both multiples of 16, c_out <= 512, kv <= 27). */
+int32_t gcd_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t kv);
+
+/* Explicit im2col for thin inputs (the 5x5x5, Cin = 1 stem): out[o, k*c_in + c] = in[nbr[k][o], c],
+ * zero where the table holds -1 and in the padding columns up to ld_out.  The stem then runs as
+ * a dense [n, ld_out] x [ld_out, c_out] product through gcd_conv_forward with an identity map. */
+int32_t gcd_im2col(const void* in, int64_t ld_in, int32_t c_in, const int32_t* nbr, int32_t kv, int64_t n_out,
+                   void* out, int64_t ld_out, int32_t in_dtype, int32_t out_dtype, void* stream);
+
+/* ------------------------------------------------------------------ batch norm ---------- */
+/* Per-channel sum / sum of squares of x [n, c] into stats [2c] fp64 (accumulated; caller zeroes). */
+int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c, int32_t dtype, double* stats, void* stream);
+/* Training-mode finalise: mean/invstd [c] fp32 from stats, running stats update
+ * (momentum, unbiased variance as nn.BatchNorm1d), scale = gamma*invstd, shift = beta - mean*scale. */
+int32_t gcd_bn_finalize(const double* stats, int64_t n, int32_t c, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var,
+                        float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* Eval-mode: scale/shift from running stats. */
+int32_t gcd_bn_fold_eval(int32_t c, const float* gamma, const float* beta, const float* running_mean,
+                         const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* y = act(x * scale + shift (+ residual)); relu = 0/1; residual may be NULL; y may alias x. */
+int32_t gcd_bn_apply(const void* x, int64_t ld_x, int64_t n, int32_t c, const float* scale, const float* shift,
+                     const void* residual, int64_t ld_res, int32_t relu, void* y, int64_t ld_y,
+                     int32_t dtype, void* stream);
+/* Backward of y = act(bn(x) + residual) in training mode.
+ *  pass 1 (reduce): g = dy * (y > 0 if relu); sums[0:c] += sum g, sums[c:2c] += sum g * xhat  (fp64)
+ *  pass 2 (apply):  dx = gamma*invstd * (g - sum_g/n - xhat * sum_gxhat/n); dres = g (optional);
+ *                   dgamma = sum_gxhat, dbeta = sum_g (accumulated into dgamma/dbeta, fp32). */
+int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
+                               int64_t n, int32_t c, const float* mean, const float* invstd, int32_t relu,
+                               int32_t dtype, double* sums, void* stream);
+int32_t gcd_bn_backward_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
+                              int64_t n, int32_t c, const float* mean, const float* invstd, const float* gamma,
+                              const double* sums, int32_t relu, int32_t training, void* dx, int64_t ld_dx,
+                              void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream);
+/* y = max(x, 0) and its backward, for stand-alone MinkowskiReLU. */
+int32_t gcd_relu(const void* x, void* y, int64_t numel, int32_t dtype, void* stream);
+int32_t gcd_relu_backward(const void* dy, const void* y, void* dx, int64_t numel, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------ voxel <-> point ----- */
+/* out[p, :] = in[idx[p], :]  (devoxelisation gather; idx int64). */
+int32_t gcd_rows_gather(const float* in, int64_t ld_in, const int64_t* idx, int64_t n_out, int32_t c,
+                        float* out, int64_t ld_out, void* stream);
+size_t gcd_csr_workspace_bytes(int64_t n_points, int64_t n_segments);
+/* Group points by segment (counting sort, stable): seg_off [n_segments+1] int32, order [n_points] int32
+ * lists the points of segment s at order[seg_off[s]:seg_off[s+1]] in ascending point index. */
+int32_t gcd_csr_build(const int64_t* idx, int64_t n_points, int64_t n_segments, int32_t* seg_off,
+                      int32_t* order, void* workspace, size_t workspace_bytes, void* stream);
+/* out[s, :] = reduce over the points of segment s of in[p, :]; mode 0 sum, 1 mean, 2 max
+ * (empty segments give 0).  The backward of gcd_rows_gather is mode 0. */
+int32_t gcd_segment_reduce(const float* in, int64_t ld_in, const int32_t* seg_off, const int32_t* order,
+                           int64_t n_segments, int32_t c, int32_t mode, float* out, int64_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCDLSS_B200_H_ */

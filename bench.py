@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — scans/s of the voxelise + MinkUNet hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference path's CPU restatement
+
+A step = one pass of the hot path over one batch: coordinate hash + kernel-map build for the batch,
+MinkUNet34 (Stage-1 model, ref modules/exp.py:249-267) forward, cross-entropy, backward (dgrad + wgrad),
+data-parallel gradient all-reduce, SGD update.  ``value`` times it with inputs resident in HBM;
+``e2e`` times the public API from pinned HOST point clouds (H2D copy, GPU quantise + dedup, the step,
+D2H of the loss).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import _paths  # noqa: E402,F401
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (scan kind, scans per GPU, points per scan (None = full sweep), classes)
+    "kitti_b4": ("kitti", 4, None, 17),          # BASELINE.json configs[1]
+    "nuscenes_b16": ("nuscenes", 16, None, 14),  # configs[2]
+}
+METRIC = "MinkUNet fwd+bwd scans/sec"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ data
+def make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches):
+    """Pinned host point clouds [N, 4] (x, y, z, remission) + per-point labels, ``n_batches`` distinct batches."""
+    from gcdlss_b200 import synth
+    batches = []
+    for b in range(n_batches):
+        scans = []
+        for s in range(scans_per_gpu):
+            idx = (rank * n_batches + b) * scans_per_gpu + s
+            xyz, feat = synth.make_scan(kind, idx, n_points=n_points)
+            pts = torch.from_numpy(np.concatenate([xyz, feat], 1)).pin_memory()
+            lab = torch.from_numpy(np.random.default_rng(idx).integers(0, n_classes, xyz.shape[0])).pin_memory()
+            scans.append((pts, lab))
+        batches.append(scans)
+    return batches
+
+
+def quantize_batch_on_gpu(scans, q, dev):
+    """H2D + GPU quantise/dedup of one batch -> (bcoords int32 [M,4], feats [M,1], labels [M]) on the device."""
+    from gcdlss_b200.quantize import sparse_quantize_gpu
+    coords, feats, labels = [], [], []
+    for b, (pts, lab) in enumerate(scans):
+        p = pts.to(dev, non_blocking=True)
+        l = lab.to(dev, non_blocking=True)
+        c, um, _ = sparse_quantize_gpu(p[:, :3], q)
+        coords.append(torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int32, device=dev), c], 1))
+        feats.append(p[:, 3:4].index_select(0, um))
+        labels.append(l.index_select(0, um))
+    return torch.cat(coords), torch.cat(feats), torch.cat(labels)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def oracle_scan_step(kind, index, n_points, n_classes, params, arch):
+    """One scan through the CPU restatement: quantise (numpy) + MinkUNet fwd + CE + bwd (torch CPU)."""
+    from gcdlss_b200 import synth
+    from oracle import quantize as oq
+    from oracle.minkunet import OracleMinkUNet
+    xyz, feat = synth.make_scan(kind, index, n_points=n_points)
+    c, um, _ = oq.sparse_quantize_me(xyz, synth.voxel_size(kind))
+    bc = oq.batched_coordinates([c])
+    labels = torch.from_numpy(np.random.default_rng(index).integers(0, n_classes, bc.shape[0]))
+    for p in params.values():
+        if p.is_floating_point() and p.requires_grad:
+            p.grad = None
+    logits, _, _ = OracleMinkUNet(params, arch, training=True).forward(bc, torch.from_numpy(feat[um]))
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    return float(loss)
+
+
+def oracle_params(n_classes):
+    from models import minkunet as mu
+    torch.manual_seed(1234)
+    model = mu.MinkUNet34C(1, n_classes)
+    params = {}
+    for k, v in model.state_dict().items():
+        params[k] = v.clone()
+        if v.is_floating_point() and "running" not in k:
+            params[k].requires_grad_(True)
+    return params
+
+
+def time_reference(kind, n_points, n_classes, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = oracle_params(n_classes)
+    for i in range(warmup):
+        oracle_scan_step(kind, i, n_points, n_classes, params, "MinkUNet34C")
+    t0 = time.perf_counter()
+    for i in range(steps):
+        oracle_scan_step(kind, 100 + i, n_points, n_classes, params, "MinkUNet34C")
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return 1.0 / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, scans, n_points, n_classes = WORKLOADS[args.workload]
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    sps, dt, cores = time_reference(kind, n_points, n_classes, steps, warmup)
+    sample = f"{steps} steps of 1 {kind}-like scan each (quantise + MinkUNet34C fwd + CE + bwd), torch CPU fp32, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "scans/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "CPU restatement of the reference path (MinkowskiEngine itself is not installable here)"},
+            "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    import gcdlss_b200
+    import MinkowskiEngine as ME
+    from gcdlss_b200 import ops, synth
+    from gcdlss_b200.ddp import GradBucketReducer
+    from models.multiheadminkunet import MinkUNetBase
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    gcdlss_b200.set_math_mode("bf16" if args.dtype == "bf16" else "fp32")
+    kind, scans_per_gpu, n_points, n_classes = WORKLOADS[args.workload]
+    q = synth.voxel_size(kind)
+    peaks = load_peaks()
+
+    torch.manual_seed(1234)
+    model = MinkUNetBase(num_classes=n_classes).to(dev).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)     # ref modules/exp.py:155-174
+    reducer = GradBucketReducer(model.parameters())
+
+    n_batches = 3
+    host_batches = make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches)
+    resident = [quantize_batch_on_gpu(b, q, dev) for b in host_batches]
+    torch.cuda.synchronize()
+    h2d_bytes = int(np.mean([sum(p.numel() * 4 + l.numel() * 8 for p, l in b) for b in host_batches]))
+    voxels = int(np.mean([r[0].shape[0] for r in resident]))
+    points = int(np.mean([sum(p.shape[0] for p, _ in b) for b in host_batches]))
+
+    def train_step(bcoords, feats, labels):
+        st = ME.SparseTensor(features=feats, coordinates=bcoords)
+        out = model(st)
+        loss = torch.nn.functional.cross_entropy(out["logits"], labels)
+        reducer.reset()
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def step_resident(i):
+        return train_step(*resident[i % n_batches])
+
+    def step_e2e(i):
+        loss = train_step(*quantize_batch_on_gpu(host_batches[i % n_batches], q, dev))
+        return float(loss.item())             # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step_resident(i)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ops.launch_counter["calls"]
+    ops.kernel_timer.enabled = True
+    ops.kernel_timer.records.clear()
+    total_ms = timed(step_resident, args.steps)
+    ops.kernel_timer.enabled = False
+    launches = ops.launch_counter["calls"] - launches0
+    if args.no_e2e:
+        e2e_ms = float("nan")
+    else:
+        for i in range(min(args.warmup, 3)):
+            step_e2e(i)
+        e2e_ms = timed(step_e2e, args.steps)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    scans_total = scans_per_gpu * world * args.steps
+    value = scans_total / (total_ms / 1e3)
+    e2e_value = scans_total / (e2e_ms / 1e3)
+
+    # ---- live roofline of the dominant kernel class (events recorded inside the timed region) ----
+    roofline = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        pair_cache = {}
+        agg = {}
+        for kind_k, ptr, n_out, kv, c_in, c_out, e0, e1 in ops.kernel_timer.records:
+            dur = e0.elapsed_time(e1) * 1e-3
+            agg.setdefault(kind_k, {"time": 0.0, "flops": 0.0, "launches": 0, "recs": []})
+            agg[kind_k]["time"] += dur
+            agg[kind_k]["launches"] += 1
+            agg[kind_k]["recs"].append((ptr, n_out, kv, c_in, c_out))
+        # exact pair counts of the maps used (computed after timing; identity maps have n_out pairs)
+        live = {}
+        for bc, _, _ in resident:
+            pass
+        top = max(agg.items(), key=lambda kv_: kv_[1]["time"]) if agg else None
+        if top is not None:
+            name, info = top
+            # density of real kernel maps is measured once on a fresh tensor of batch 0
+            st = ME.SparseTensor(features=resident[0][1], coordinates=resident[0][0])
+            dens = {}
+            mgr = st.coordinate_manager
+            for ts in (1, 2, 4, 8, 16):
+                mgr.get_map(ts)
+            for key in [(ts, 3, 1, False) for ts in (1, 2, 4, 8, 16)] + [(ts, 2, 2, False) for ts in (1, 2, 4, 8)] + [(ts, 2, 2, True) for ts in (2, 4, 8, 16)]:
+                km = mgr.kernel_map(*key)
+                dens[(km.kv, km.n_out)] = km.num_pairs()
+            flops = 0.0
+            for ptr, n_out, kv, c_in, c_out in info["recs"]:
+                pairs = n_out if ptr == 0 else dens.get((kv, n_out))
+                if pairs is None:           # another batch of the rotation: same shape class, scale by rows
+                    ref = [(k, v) for k, v in dens.items() if k[0] == kv]
+                    k0, v0 = min(ref, key=lambda t: abs(t[0][1] - n_out))
+                    pairs = v0 * n_out / k0[1]
+                flops += 2.0 * pairs * c_in * c_out
+            tensor = name.endswith("_tc")
+            peak = peaks["bf16_tflops_sustained"] if tensor else None
+            achieved = flops / info["time"] / 1e12 if info["time"] > 0 else 0.0
+            roofline = {"kernel": {"conv_tc": "conv_fwd_tc_kernel (forward + dgrad launches)", "wgrad_tc": "conv_wgrad_tc_kernel",
+                                   "conv_simt": "conv_fwd_simt_kernel", "wgrad_simt": "conv_wgrad_simt_kernel"}[name],
+                        "bound": "tensor", "achieved": achieved, "peak": peak if peak else 75.0, "unit": "TFLOP/s",
+                        "frac": achieved / (peak if peak else 75.0), "traffic": None,
+                        "peak_source": (peaks["source"] + " bf16_tflops_sustained") if tensor else "nominal fp32 FMA peak (SIMT path)",
+                        "launches_per_step": info["launches"] / args.steps, "avg_launch_us": info["time"] / info["launches"] * 1e6,
+                        "share_of_step": info["time"] / (total_ms / 1e3),
+                        "by_kernel": {k: {"time_share": v["time"] / (total_ms / 1e3), "launches_per_step": v["launches"] / args.steps} for k, v in agg.items()}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, dt, cores = time_reference(kind, n_points, n_classes, 1, 1)
+        cpu_baseline = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
+                        "sample": f"1 warm-up + 1 timed {kind}-like scan (quantise + MinkUNet34C fwd + CE + bwd) through the CPU oracle, torch CPU fp32, {cores} threads"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "scans_per_gpu": scans_per_gpu, "points_per_batch": points, "voxels_per_batch": voxels,
+                           "model": "MinkUNet34RC backbone + final head (Stage-1 MinkUNetBase)", "classes": n_classes,
+                           "step": "hash + kernel maps + fwd + CE + bwd + grad all-reduce + SGD", "parallelism": f"dp{world}",
+                           "l2": f"{n_batches} distinct batches rotate; per-step activations + maps exceed the 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + 8 * scans_per_gpu,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
+                "grad_allreduce_bytes": reducer.grad_bytes() if world > 1 else 0}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti_b4", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,81 @@
+"""Data-parallel gradient exchange: the one collective of the hot path.
+
+Scans shard across ranks with no forward communication (BN statistics are per GPU, as in the
+reference, which has no SyncBN).  After the wgrad kernels of a bucket have run, its flat fp32
+gradient buffer is all-reduced over NCCL (NVLink 5 / NVSwitch) while backward continues on the
+remaining layers.  Parameters' ``.grad`` are views into the flat buffers, so nothing is copied.
+
+Equivalent of what ``pl.Trainer(gpus=-1)`` sets up implicitly in the reference (ref main.py:286-293).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucketReducer:
+    def __init__(self, params, bucket_bytes: int = 32 << 20, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets = []            # (flat tensor, [params])
+        self._owner = {}
+        self._pending = []
+        self._handles = []
+        # reverse registration order ~ the order gradients become ready in backward
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self._close(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self._close(cur)
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._on_grad_ready)
+        self.reset()
+
+    def _close(self, plist):
+        n = sum(p.numel() for p in plist)
+        flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
+        off = 0
+        for p in plist:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self._owner[p] = len(self.buckets)
+        self.buckets.append((flat, list(plist)))
+
+    def reset(self):
+        """Zero the flat gradients and re-arm the per-bucket counters (call before each backward)."""
+        for flat, _ in self.buckets:
+            flat.zero_()
+        self._pending = [len(pl) for _, pl in self.buckets]
+        self._handles = []
+
+    def _on_grad_ready(self, p):
+        b = self._owner[p]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.world > 1:
+            self._handles.append(dist.all_reduce(self.buckets[b][0], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Wait for the outstanding all-reduces and turn sums into means."""
+        if self.world > 1:
+            for b, left in enumerate(self._pending):       # parameters that received no gradient this step
+                if left > 0:
+                    self._handles.append(dist.all_reduce(self.buckets[b][0], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for h in self._handles:
+                h.wait()
+            for flat, _ in self.buckets:
+                flat.div_(self.world)
+        self._handles = []
+
+    def grad_bytes(self) -> int:
+        return sum(f.numel() * 4 for f, _ in self.buckets)
+
+
+def shard_scans(n_scans_global: int, rank: int, world: int):
+    """Indices of the scans rank ``rank`` processes (contiguous blocks, like a DistributedSampler without shuffle)."""
+    per = n_scans_global // world
+    return list(range(rank * per, (rank + 1) * per))

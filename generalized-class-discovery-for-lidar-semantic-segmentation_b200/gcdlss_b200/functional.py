@@ -5,6 +5,8 @@ autograd graph, device memory and the stream.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -14,17 +16,20 @@ from .config import get_math_mode
 _pack_cache = {}
 
 
-def _packed(weight3: torch.Tensor, transpose: bool, mirror: bool):
-    """bf16 operand image of a kernel, re-packed only when the parameter changed."""
-    key = (weight3.data_ptr(), transpose, mirror)
-    ver = weight3._version
+def _packed(weight: torch.Tensor, transpose: bool, mirror: bool):
+    """bf16 operand image of a kernel parameter, re-packed only when the parameter changed.
+
+    Entries are validated by identity (weak reference) and version counter: a freed parameter's
+    address can be reused by a new one, so neither ``data_ptr`` nor ``id`` alone is a safe key."""
+    key = (id(weight), transpose, mirror)
     hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[1].device == weight3.device:
-        return hit[1]
-    packed = ops.pack_weights(weight3, transpose, mirror)
-    if len(_pack_cache) > 4096:
-        _pack_cache.clear()
-    _pack_cache[key] = (ver, packed)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
+        return hit[2]
+    packed = ops.pack_weights(_as3d(weight.detach()), transpose, mirror)
+    if len(_pack_cache) > 1024:
+        for k in [k for k, v in _pack_cache.items() if v[0]() is None]:
+            del _pack_cache[k]
+    _pack_cache[key] = (weakref.ref(weight), weight._version, packed)
     return packed
 
 
@@ -47,7 +52,7 @@ class SparseConvFunction(torch.autograd.Function):
         b = bias.detach().reshape(-1) if bias is not None else None
         out = ops.conv_forward(feats.detach(), kmap.nbr, w3, kmap.n_out, bias=b, out_dtype=out_dtype,
                                math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT,
-                               w_packed=_packed(w3, False, False) if tc else None)
+                               w_packed=_packed(weight, False, False) if tc else None)
         ctx.kmap, ctx.has_bias, ctx.w_shape = kmap, bias is not None, weight.shape
         ctx.save_for_backward(feats, weight)
         return out
@@ -65,7 +70,7 @@ class SparseConvFunction(torch.autograd.Function):
             tc = _use_tc(g, c_out, c_in, kv)
             gfeats = ops.conv_forward(g, kmap.back_nbr, w3, kmap.n_in, transpose_w=True, mirror=kmap.back_mirror,
                                       out_dtype=feats.dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT,
-                                      w_packed=_packed(w3, True, kmap.back_mirror) if tc else None)
+                                      w_packed=_packed(weight, True, kmap.back_mirror) if tc else None)
         if ctx.needs_input_grad[1]:
             gw3 = torch.zeros(w3.shape, dtype=torch.float32, device=w3.device)
             gb = torch.zeros(c_out, dtype=torch.float32, device=w3.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None

@@ -40,6 +40,26 @@ def _count(n=1):
     launch_counter["calls"] += n
 
 
+class KernelTimer:
+    """Optional CUDA-event brackets around the convolution launches (bench.py's live roofline).
+    Events are recorded on the launching stream; durations are read after the timed region."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []        # (kind, nbr_ptr, n_out, kv, c_in, c_out, start_event, end_event)
+
+    def bracket(self, kind, nbr, n_out, kv, c_in, c_out):
+        if not self.enabled:
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.records.append((kind, nbr.data_ptr() if nbr is not None else 0, n_out, kv, c_in, c_out, e0, e1))
+        return e1
+
+
+kernel_timer = KernelTimer()
+
+
 def _rowmajor(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dim() == 2 and t.stride(1) == 1) or t.numel() == 0 else t.contiguous()
 
@@ -228,7 +248,10 @@ def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, b
     a.in_dtype, a.out_dtype = _dtype_code(inp), _dtype_code(out)
     a.stats = stats.data_ptr() if stats is not None else None
     a.math_mode = math_mode
+    end = kernel_timer.bracket("conv_tc" if math_mode == MATH_BF16_TC else "conv_simt", nbr, n_out, kv, k_dim, n_dim)
     call("gcd_conv_forward", C.byref(a), _stream())
+    if end is not None:
+        end.record()
     _count()
     return out
 
@@ -252,7 +275,11 @@ def conv_wgrad(inp, gout, pairs, kv: int, dw: torch.Tensor, dbias=None, math_mod
     a.n_out = gout.shape[0]
     a.in_dtype, a.gout_dtype = _dtype_code(inp), _dtype_code(gout)
     a.math_mode = math_mode
+    end = kernel_timer.bracket("wgrad_tc" if math_mode == MATH_BF16_TC else "wgrad_simt", pairs[0] if pairs is not None else None,
+                               gout.shape[0], kv, inp.shape[1], gout.shape[1])
     call("gcd_conv_wgrad", C.byref(a), _stream())
+    if end is not None:
+        end.record()
     _count(2 if dbias is not None else 1)
 
 

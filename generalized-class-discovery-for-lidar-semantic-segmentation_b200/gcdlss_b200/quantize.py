@@ -118,3 +118,11 @@ def voxelize_minkunet(points, voxel_size, batch_first: bool = True, max_voxels=N
         p2v.append(inverse)
         vinds.append(inds)
     return {"voxels": torch.cat(voxels, 0), "coors": torch.cat(coors, 0), "point2voxel_maps": p2v, "voxel_inds": vinds}
+
+
+def sparse_quantize_gpu(points: torch.Tensor, quantization_size: float):
+    """GPU-resident variant: CUDA points [N, 3|4] in, (voxel coords int32 [M, D], unique_map [M], inverse_map [N])
+    out, everything left on the device (no host round trip of the maps)."""
+    ic = ops.quantize(points, float(quantization_size), points.shape[1], ROUND_FLOOR)
+    unique_idx, inverse, _ = ops.unique_rows(ic, order=0)
+    return ic.index_select(0, unique_idx), unique_idx, inverse

@@ -1,0 +1,86 @@
+"""CUDA coordinate maps / kernel maps vs the oracle: bit exact."""
+import numpy as np
+import pytest
+import torch
+
+import _paths  # noqa: F401
+from conftest import small_cloud
+from oracle import coords as ocd
+from oracle import quantize as oq
+
+pytestmark = pytest.mark.gpu
+
+
+def build_manager(bc):
+    from gcdlss_b200.coords import CoordinateManager
+    return CoordinateManager(torch.from_numpy(bc).cuda())
+
+
+def check_levels(mgr, lv):
+    for l in range(1, 5):
+        m = mgr.get_map(1 << l)
+        np.testing.assert_array_equal(m.coords.cpu().numpy(), lv.coords[l])
+        fine = mgr.get_map(1 << (l - 1))
+        np.testing.assert_array_equal(fine.parent.cpu().numpy(), lv.parent[l - 1])
+        np.testing.assert_array_equal(fine.code.cpu().numpy(), lv.code[l - 1])
+    for l in range(5):
+        km = mgr.kernel_map(1 << l, 3, 1, False)
+        np.testing.assert_array_equal(km.nbr.cpu().numpy().T, lv.subm(l, 3))
+    np.testing.assert_array_equal(mgr.kernel_map(1, 5, 1, False).nbr.cpu().numpy().T, lv.subm(0, 5))
+    for l in range(4):
+        np.testing.assert_array_equal(mgr.kernel_map(1 << l, 2, 2, False).nbr.cpu().numpy().T, lv.down(l))
+        np.testing.assert_array_equal(mgr.kernel_map(2 << l, 2, 2, True).nbr.cpu().numpy().T, lv.up(l))
+
+
+def test_maps_match_frozen_fixture(cuda, oracle_frozen):
+    bc = oracle_frozen["map_coords0"]
+    mgr = build_manager(bc)
+    lv = ocd.CoordLevels(bc)
+    for l in range(1, 5):                                   # oracle itself still equals the frozen file
+        np.testing.assert_array_equal(lv.coords[l], oracle_frozen[f"map_coords{l}"])
+    check_levels(mgr, lv)
+
+
+def test_maps_kitti_batch(cuda):
+    from gcdlss_b200 import synth
+    scans = [oq.sparse_quantize_me(synth.make_scan("kitti", i, n_points=20000)[0], 0.05)[0] for i in range(2)]
+    bc = oq.batched_coordinates(scans)
+    check_levels(build_manager(bc), ocd.CoordLevels(bc))
+
+
+def test_pair_lists(cuda):
+    bc = small_cloud(4, 3000, spread=0.6, batch=0)
+    mgr = build_manager(bc)
+    lv = ocd.CoordLevels(bc)
+    for km, table in ((mgr.kernel_map(1, 3, 1, False), lv.subm(0, 3)), (mgr.kernel_map(1, 2, 2, False), lv.down(0)),
+                      (mgr.kernel_map(2, 2, 2, True), lv.up(0))):
+        pi, po, off = ocd.pairs_from_table(table)
+        gi, go, goff = km.pairs
+        np.testing.assert_array_equal(goff.cpu().numpy(), off)
+        np.testing.assert_array_equal(gi.cpu().numpy()[: off[-1]], pi)
+        np.testing.assert_array_equal(go.cpu().numpy()[: off[-1]], po)
+        assert km.num_pairs() == off[-1]
+
+
+def test_lasermix_batch_ids_and_negative_coords(cuda):
+    # batch ids 0,20,40,60 (ref exp_merge_mean_teacher.py:2856 quirk) and negative coordinates
+    parts = [small_cloud(10 + i, 500, spread=0.5, batch=20 * i) for i in range(4)]
+    bc = np.concatenate(parts)
+    check_levels(build_manager(bc), ocd.CoordLevels(bc))
+
+
+def test_duplicate_and_range_errors(cuda):
+    import MinkowskiEngine as ME
+    c = torch.tensor([[0, 1, 2, 3], [0, 1, 2, 3]], dtype=torch.int32).cuda()
+    st = ME.SparseTensor(features=torch.ones(2, 1).cuda(), coordinates=c)
+    with pytest.raises(RuntimeError, match="duplicate"):
+        st.C
+    c = torch.tensor([[0, 1 << 20, 2, 3]], dtype=torch.int32).cuda()
+    with pytest.raises(RuntimeError, match="64-bit key"):
+        ME.SparseTensor(features=torch.ones(1, 1).cuda(), coordinates=c).C
+
+
+def test_tiny_inputs(cuda):
+    bc = np.array([[0, -3, 5, 7]], np.int32)
+    mgr = build_manager(bc)
+    check_levels(mgr, ocd.CoordLevels(bc))

@@ -18,6 +18,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # scan sizes vary step to step: avoid cudaMalloc churn
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import _paths  # noqa: E402,F401
@@ -198,7 +200,7 @@ def run_ours(args):
 
     torch.manual_seed(1234)
     model = MinkUNetBase(num_classes=n_classes).to(dev).train()
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)     # ref modules/exp.py:155-174
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, fused=True)     # ref modules/exp.py:155-174
     reducer = GradBucketReducer(model.parameters())
 
     n_batches = 3
@@ -244,8 +246,31 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 2 * n_batches + 2)):      # at least W; every batch shape seen twice before timing
         step_resident(i)
+    import gc
+    gc.collect()
+    gc.freeze()            # model / maps / library objects are long-lived: keep the cyclic GC from re-walking them every few steps
+    if args.debug_steps and rank == 0:
+        gc_t = [0.0, 0.0]
+
+        def _gc_cb(phase, info):
+            if phase == "start":
+                gc_t[1] = time.perf_counter()
+            else:
+                gc_t[0] += time.perf_counter() - gc_t[1]
+        gc.callbacks.append(_gc_cb)
+        for i in range(12):
+            ms0 = torch.cuda.memory_stats()
+            gc_t[0] = 0.0
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            step_resident(i)
+            t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+            ms1 = torch.cuda.memory_stats()
+            print(f"debug step {i}: host {1e3 * (t1 - t0):.2f} ms, total {1e3 * (t2 - t0):.2f} ms, gc {1e3 * gc_t[0]:.2f} ms, "
+                  f"segments +{ms1['segment.all.allocated'] - ms0['segment.all.allocated']}, reserved {ms1['reserved_bytes.all.current'] >> 20} MiB, "
+                  f"alloc_retries {ms1['num_alloc_retries']}", file=sys.stderr)
+        gc.callbacks.remove(_gc_cb)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -347,6 +372,7 @@ def main():
     ap.add_argument("--workload", default="kitti_b4", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-steps", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -271,6 +271,39 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   const int64_t off = img + (int64_t)n * kChunkK + ((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7));
   packed[off] = __float2bfloat16_rn(v);
 }
+
+// All kernels of a model in one launch: block b works on descriptor d with block_start[d] <= b < block_start[d+1].
+struct PackDesc {
+  const float* w;
+  __nv_bfloat16* dst;
+  int32_t kv, c_in, c_out, transpose, mirror;
+  int32_t block_start;
+};
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackDesc* __restrict__ descs, int n_descs) {
+  int lo = 0, hi = n_descs - 1;
+  while (lo < hi) {                       // last descriptor whose block_start <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackDesc d = descs[lo];
+  const int kdim = d.transpose ? d.c_out : d.c_in, ndim = d.transpose ? d.c_in : d.c_out;
+  const int nq = (kdim + kChunkK - 1) / kChunkK;
+  const int64_t total = (int64_t)d.kv * nq * ndim * kChunkK;
+  const int64_t t = (int64_t)(blockIdx.x - d.block_start) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int kk = (int)(t % kChunkK);
+  const int n = (int)((t / kChunkK) % ndim);
+  const int q = (int)((t / ((int64_t)kChunkK * ndim)) % nq);
+  const int k = (int)(t / ((int64_t)kChunkK * ndim * nq));
+  const int c = q * kChunkK + kk;
+  float v = 0.f;
+  if (c < kdim) {
+    const int ksrc = (d.transpose && d.mirror) ? d.kv - 1 - k : k;
+    v = d.transpose ? d.w[((int64_t)ksrc * d.c_in + n) * d.c_out + c] : d.w[((int64_t)ksrc * d.c_in + c) * d.c_out + n];
+  }
+  const int64_t img = ((int64_t)k * nq + q) * ndim * kChunkK;
+  d.dst[img + (int64_t)n * kChunkK + ((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7))] = __float2bfloat16_rn(v);
+}
 }  // namespace
 
 
@@ -552,6 +585,14 @@ extern "C" int32_t gcd_conv_pack_weights(const float* w, int32_t kv, int32_t c_i
   const int64_t total = (int64_t)kv * ((kdim + 63) / 64) * ndim * 64;
   pack_weights_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, kv, c_in, c_out, transpose, mirror, (__nv_bfloat16*)packed);
   GCD_LAUNCH_CHECK("gcd_conv_pack_weights");
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_conv_pack_weights_batched(const void* descs, int32_t n_descs, int32_t total_blocks, void* stream) {
+  GCD_REQUIRE(descs && n_descs >= 1 && total_blocks >= 1, "gcd_conv_pack_weights_batched: bad arguments");
+  static_assert(sizeof(PackDesc) == 40, "PackDesc layout is part of the C ABI (gcd_pack_desc)");
+  pack_weights_batched_kernel<<<(unsigned)total_blocks, 256, 0, as_stream(stream)>>>((const PackDesc*)descs, n_descs);
+  GCD_LAUNCH_CHECK("gcd_conv_pack_weights_batched");
   return GCD_OK;
 }
 

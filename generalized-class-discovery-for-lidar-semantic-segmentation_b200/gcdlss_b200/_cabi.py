@@ -99,6 +99,7 @@ PROTOTYPES = {
     "gcd_conv_packed_weight_bytes": (_sz, [_i32, _i32, _i32]),
     "gcd_conv_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "gcd_conv_wgrad": (_i32, [C.POINTER(WgradArgs), _vp]),
+    "gcd_conv_pack_weights_batched": (_i32, [_vp, _i32, _i32, _vp]),
     "gcd_conv_tc_supported": (_i32, [_i32, _i32, _i32]),
     "gcd_im2col": (_i32, [_vp, _i64, _i32, _vp, _i32, _i64, _vp, _i64, _i32, _i32, _vp]),
     "gcd_bn_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
@@ -140,6 +141,14 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"libgcdlss_sm100a {what} failed (code {rc}): {msg}")
 
 
+_fn_cache = {}
+
+
 def call(name: str, *args):
     """Call an int32-status entry point and raise on a non-zero return."""
-    check(getattr(lib(), name)(*args), name)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)
+    rc = fn(*args)
+    if rc != 0:
+        check(rc, name)

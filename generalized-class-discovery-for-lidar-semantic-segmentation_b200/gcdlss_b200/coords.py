@@ -7,6 +7,8 @@ tensor derived from it, so a teacher and a student that consume the same input t
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -24,14 +26,16 @@ class CoordMap:
 class KernelMap:
     """A dense neighbour table plus, lazily, its per-offset pair lists.
 
-    nbr [kv, n_out] int32 feeds the output-stationary forward; ``back`` names the table and weight
-    orientation of the matching dgrad (see include/gcdlss_b200.h, gcd_conv_args)."""
+    nbr [kv, n_out] int32 feeds the output-stationary forward; ``back_key`` names the kernel map whose
+    table drives the matching dgrad (see include/gcdlss_b200.h, gcd_conv_args).  The manager is held
+    weakly: maps must die by reference counting when the batch's tensors die (a manager <-> map cycle
+    would park hundreds of MB per step until the cyclic GC runs)."""
 
-    def __init__(self, nbr, n_in, n_out, kv, back_nbr_fn, back_mirror):
+    def __init__(self, nbr, n_in, n_out, kv, manager, back_key, back_mirror):
         self.nbr, self.n_in, self.n_out, self.kv = nbr, n_in, n_out, kv
-        self._back_nbr_fn, self.back_mirror = back_nbr_fn, back_mirror
+        self._mgr = weakref.ref(manager)
+        self._back_key, self.back_mirror = back_key, back_mirror
         self._pairs = None
-        self._back = None
 
     @property
     def pairs(self):
@@ -41,9 +45,14 @@ class KernelMap:
 
     @property
     def back_nbr(self):
-        if self._back is None and self._back_nbr_fn is not None:
-            self._back = self._back_nbr_fn()
-        return self._back
+        if self._back_key is None:
+            return None
+        if self._back_key == "self":
+            return self.nbr
+        mgr = self._mgr()
+        if mgr is None:
+            raise RuntimeError("the coordinate manager of this kernel map no longer exists")
+        return mgr.kernel_map(*self._back_key).nbr
 
     def num_pairs(self) -> int:
         """Exact pair count (one device read; used for FLOP accounting only)."""
@@ -57,6 +66,7 @@ class CoordinateManager:
         if coords.dim() != 2 or coords.shape[1] != 4:
             raise ValueError("coordinates must be [N, 4] (batch, x, y, z)")
         coords = coords.to(torch.int32).contiguous()
+        ops.new_batch()
         self.device = coords.device
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.maps = {1: CoordMap(coords, ops.hash_build(coords, self.status), 1)}
@@ -86,17 +96,17 @@ class CoordinateManager:
             return km
         if kernel_size == 1 and stride == 1:
             m = self.get_map(ts_in)
-            km = KernelMap(None, m.n, m.n, 1, None, False)
+            km = KernelMap(None, m.n, m.n, 1, self, None, False)
         elif stride == 1 and kernel_size in (3, 5) and not transposed:
             m = self.get_map(ts_in)
             nbr = ops.kmap_subm(m.coords, m.table, kernel_size, ts_in)
             # stride-1 symmetric kernel: the transposed map is the same table with mirrored offsets
-            km = KernelMap(nbr, m.n, m.n, kernel_size ** 3, lambda: nbr, True)
+            km = KernelMap(nbr, m.n, m.n, kernel_size ** 3, self, "self", True)
         elif stride == 2 and kernel_size == 2 and not transposed:
             fine = self.get_map(ts_in)
             coarse = self.get_map(ts_in * 2)
             nbr = ops.kmap_down2(fine.parent, fine.code, coarse.n)
-            km = KernelMap(nbr, fine.n, coarse.n, 8, lambda: self.kernel_map(ts_in * 2, 2, 2, True).nbr, False)
+            km = KernelMap(nbr, fine.n, coarse.n, 8, self, (ts_in * 2, 2, 2, True), False)
         elif stride == 2 and kernel_size == 2 and transposed:
             if ts_in % 2 or ts_in // 2 not in self.maps:
                 raise RuntimeError("transposed convolution needs the finer coordinate map to exist already "
@@ -104,7 +114,7 @@ class CoordinateManager:
             fine = self.get_map(ts_in // 2)
             coarse = self.get_map(ts_in)
             nbr = ops.kmap_up2(fine.parent, fine.code)
-            km = KernelMap(nbr, coarse.n, fine.n, 8, lambda: self.kernel_map(ts_in // 2, 2, 2, False).nbr, False)
+            km = KernelMap(nbr, coarse.n, fine.n, 8, self, (ts_in // 2, 2, 2, False), False)
         else:
             raise NotImplementedError(f"kernel_size={kernel_size}, stride={stride}, transposed={transposed} is not on the "
                                       "MinkUNet path (supported: 1/1, 3/1, 5/1, 2/2 and transposed 2/2)")

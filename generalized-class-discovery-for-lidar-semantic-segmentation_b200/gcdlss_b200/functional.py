@@ -13,24 +13,58 @@ from . import ops
 from ._cabi import MATH_BF16_TC, MATH_FP32_SIMT
 from .config import get_math_mode
 
-_pack_cache = {}
+class PackedWeights:
+    """bf16 tcgen05 operand images (forward and dgrad orientation) of every convolution module, kept in
+    persistent device buffers and refreshed by ONE batched launch when parameters changed (i.e. once per
+    optimiser / EMA step) instead of two small launches per layer."""
+
+    def __init__(self):
+        self.modules = weakref.WeakSet()
+        self._sig = None
+        self._table = None
+
+    def register(self, module):
+        self.modules.add(module)
+
+    @staticmethod
+    def _stale(m, dev):
+        w = m.kernel
+        return w.device == dev and (m._pk_version != w._version or m._pk_ptr != w.data_ptr())
+
+    def ensure(self, module):
+        w = module.kernel
+        if module._pk_version == w._version and module._pk_ptr == w.data_ptr():
+            return
+        dev = w.device
+        self.modules.add(module)            # deep-copied modules (EMA teacher) never ran __init__
+        stale = [m for m in self.modules if m._pk_tc and self._stale(m, dev)]
+        if module not in stale:
+            stale.append(module)
+        recs, blocks = [], 0
+        for m in stale:
+            kv, cin, cout = m.kernel_volume, m.in_channels, m.out_channels
+            if m._pk_fwd is None or m._pk_fwd.device != dev:
+                nbytes = int(ops.lib().gcd_conv_packed_weight_bytes(kv, cin, cout))
+                m._pk_fwd = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                m._pk_bwd = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            for dst, transpose, kdim, ndim in ((m._pk_fwd, 0, cin, cout), (m._pk_bwd, 1, cout, cin)):
+                recs.append((m.kernel.data_ptr(), dst.data_ptr(), kv, cin, cout, transpose, int(m._pk_mirror and transpose), blocks))
+                blocks += (kv * ((kdim + 63) // 64) * ndim * 64 + 255) // 256
+        sig = tuple(r[:2] for r in recs)
+        if sig != self._sig or self._table is None or self._table.device != dev:
+            import numpy as np
+            host = np.zeros(len(recs), dtype=np.dtype([("w", "<u8"), ("dst", "<u8"), ("kv", "<i4"), ("c_in", "<i4"), ("c_out", "<i4"),
+                                                         ("transpose", "<i4"), ("mirror", "<i4"), ("block_start", "<i4")]))
+            for i, r in enumerate(recs):
+                host[i] = r
+            self._table = torch.from_numpy(host.view(np.uint8).copy()).to(dev)
+            self._sig = sig
+        ops.pack_weights_batched(self._table, len(recs), blocks)
+        for m in stale:
+            m._pk_version, m._pk_ptr = m.kernel._version, m.kernel.data_ptr()
 
 
-def _packed(weight: torch.Tensor, transpose: bool, mirror: bool):
-    """bf16 operand image of a kernel parameter, re-packed only when the parameter changed.
-
-    Entries are validated by identity (weak reference) and version counter: a freed parameter's
-    address can be reused by a new one, so neither ``data_ptr`` nor ``id`` alone is a safe key."""
-    key = (id(weight), transpose, mirror)
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
-        return hit[2]
-    packed = ops.pack_weights(_as3d(weight.detach()), transpose, mirror)
-    if len(_pack_cache) > 1024:
-        for k in [k for k, v in _pack_cache.items() if v[0]() is None]:
-            del _pack_cache[k]
-    _pack_cache[key] = (weakref.ref(weight), weight._version, packed)
-    return packed
+packed_weights = PackedWeights()
 
 
 def _as3d(weight: torch.Tensor) -> torch.Tensor:
@@ -45,15 +79,21 @@ class SparseConvFunction(torch.autograd.Function):
     """out[o] = sum_k feats[nbr[k,o]] @ W[k] (+ bias).  ``kmap`` is a coords.KernelMap."""
 
     @staticmethod
-    def forward(ctx, feats, weight, bias, kmap, out_dtype):
+    def forward(ctx, feats, weight, bias, kmap, out_dtype, holder=None):
         w3 = _as3d(weight.detach())
         kv, c_in, c_out = w3.shape
         tc = _use_tc(feats, c_in, c_out, kv)
         b = bias.detach().reshape(-1) if bias is not None else None
+        packed = None
+        if tc:
+            if holder is not None:
+                packed_weights.ensure(holder)
+                packed = holder._pk_fwd
+            else:
+                packed = ops.pack_weights(w3, False, False)
         out = ops.conv_forward(feats.detach(), kmap.nbr, w3, kmap.n_out, bias=b, out_dtype=out_dtype,
-                               math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT,
-                               w_packed=_packed(weight, False, False) if tc else None)
-        ctx.kmap, ctx.has_bias, ctx.w_shape = kmap, bias is not None, weight.shape
+                               math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed)
+        ctx.kmap, ctx.has_bias, ctx.w_shape, ctx.holder = kmap, bias is not None, weight.shape, holder
         ctx.save_for_backward(feats, weight)
         return out
 
@@ -68,12 +108,19 @@ class SparseConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             g = gout if gout.dtype == feats.dtype else gout.to(feats.dtype)
             tc = _use_tc(g, c_out, c_in, kv)
+            packed = None
+            if tc:
+                holder = ctx.holder
+                if holder is not None and holder._pk_mirror == kmap.back_mirror:
+                    packed_weights.ensure(holder)
+                    packed = holder._pk_bwd
+                else:
+                    packed = ops.pack_weights(w3, True, kmap.back_mirror)
             gfeats = ops.conv_forward(g, kmap.back_nbr, w3, kmap.n_in, transpose_w=True, mirror=kmap.back_mirror,
-                                      out_dtype=feats.dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT,
-                                      w_packed=_packed(weight, True, kmap.back_mirror) if tc else None)
+                                      out_dtype=feats.dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed)
         if ctx.needs_input_grad[1]:
-            gw3 = torch.zeros(w3.shape, dtype=torch.float32, device=w3.device)
-            gb = torch.zeros(c_out, dtype=torch.float32, device=w3.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+            gw3 = ops.zeros_f32.take(w3.numel(), w3.device).view(w3.shape)
+            gb = ops.zeros_f32.take(c_out, w3.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
             g = gout
             f = feats.detach()
             tc = get_math_mode() == "bf16" and f.dtype == torch.bfloat16 and ops.tc_supported(c_in, c_out, kv) and c_out <= 256
@@ -85,7 +132,7 @@ class SparseConvFunction(torch.autograd.Function):
                 gb = gb.reshape(1, -1)
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.float().sum(0, keepdim=True)
-        return gfeats, gw, gb, None, None
+        return gfeats, gw, gb, None, None, None
 
 
 class Im2colFunction(torch.autograd.Function):

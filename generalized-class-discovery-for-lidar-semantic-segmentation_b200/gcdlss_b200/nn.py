@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from . import ops
 from .config import get_math_mode
-from .functional import BatchNormActFunction, Im2colFunction, ReLUFunction, SparseConvFunction
+from .functional import BatchNormActFunction, Im2colFunction, ReLUFunction, SparseConvFunction, packed_weights
 from .sparse_tensor import CoordinateMapKey, SparseTensor
 
 
@@ -48,6 +48,12 @@ class _ConvBase(nn.Module):
         self.kernel = nn.Parameter(torch.empty(shape, dtype=torch.float32))
         self.bias = nn.Parameter(torch.empty(1, out_channels, dtype=torch.float32)) if bias else None
         self.reset_parameters()
+        # persistent bf16 operand images for the tcgen05 path (see functional.PackedWeights)
+        self._pk_fwd = self._pk_bwd = None
+        self._pk_version, self._pk_ptr = -1, 0
+        self._pk_tc = ops.tc_supported(in_channels, out_channels, self.kernel_volume)
+        self._pk_mirror = self.stride == 1 and self.kernel_volume > 1     # stride-1 maps are self-transposed with mirrored offsets
+        packed_weights.register(self)
 
     def reset_parameters(self):
         # ME default: U(-1/sqrt(fan), 1/sqrt(fan)), fan = (Cout if transposed else Cin) * K^3
@@ -99,7 +105,7 @@ class _ConvBase(nn.Module):
             out_dtype = self._out_dtype(feats, self.in_channels, self.kernel_volume)
             if bf16 and out_dtype == torch.bfloat16 and feats.dtype != torch.bfloat16:
                 feats = feats.to(torch.bfloat16)
-            out = SparseConvFunction.apply(feats, self.kernel, self.bias, kmap, out_dtype)
+            out = SparseConvFunction.apply(feats, self.kernel, self.bias, kmap, out_dtype, self)
         return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
 
     def extra_repr(self):
@@ -117,6 +123,10 @@ class MinkowskiConvolutionTranspose(_ConvBase):
     TRANSPOSED = True
 
 
+def _flush_batches_hook(module, prefix, keep_vars):
+    module._flush_batches()
+
+
 class MinkowskiBatchNorm(nn.Module):
     """``self.bn = nn.BatchNorm1d`` over all rows of F (state_dict keys ``<name>.bn.weight`` ...)."""
 
@@ -125,14 +135,24 @@ class MinkowskiBatchNorm(nn.Module):
         if not (affine and track_running_stats):
             raise NotImplementedError("only affine batch norm with running statistics is on the MinkUNet path")
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine, track_running_stats=track_running_stats)
+        # num_batches_tracked is only read by checkpoints (and momentum=None): count on the host and write the
+        # device scalar when somebody looks, instead of one tiny kernel per layer per step.
+        self._pending_batches = 0
+        self.register_state_dict_pre_hook(_flush_batches_hook)
+
+    def _flush_batches(self):
+        if self._pending_batches:
+            self.bn.num_batches_tracked.add_(self._pending_batches)
+            self._pending_batches = 0
 
     def forward(self, input: SparseTensor, relu: bool = False, residual: SparseTensor = None) -> SparseTensor:
         bn = self.bn
         training = bn.training
         momentum = bn.momentum
         if training:
-            bn.num_batches_tracked.add_(1)
+            self._pending_batches += 1
             if momentum is None:
+                self._flush_batches()
                 momentum = 1.0 / float(bn.num_batches_tracked.item())
         x = input._F
         res = None

@@ -14,8 +14,50 @@ from ._cabi import BF16, F32, MATH_BF16_TC, MATH_FP32_SIMT, ConvArgs, WgradArgs,
 launch_counter = {"calls": 0}
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_device = torch._C._cuda_getDevice
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream (raw pointer value; cheap enough to call per launch)."""
+    return _raw_stream(_cur_device())
+
+
+class ZeroArena:
+    """Hands out zero-filled scratch (per-channel statistics, weight-gradient accumulators) carved from
+    large pre-zeroed chunks, so a training step issues one memset per chunk instead of one per layer.
+    A slice is used once; a chunk is released when its last slice dies.  ``new_period`` (called when a new
+    coordinate manager, i.e. a new batch, appears) starts a fresh chunk sized to the previous period's use,
+    which keeps the allocation sequence identical from step to step (no allocator growth in steady state)."""
+
+    def __init__(self, dtype, min_chunk):
+        self.dtype, self.min_chunk, self.chunk = dtype, min_chunk, min_chunk
+        self.buf, self.off, self.used = None, 0, 0
+
+    def new_period(self):
+        if self.used:
+            self.chunk = max(self.min_chunk, (int(self.used * 1.02) + 4095) & ~4095)
+        self.buf, self.off, self.used = None, 0, 0
+
+    def take(self, n: int, device) -> torch.Tensor:
+        n_al = (n + 3) & ~3
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            self.buf = torch.zeros(max(self.chunk, n_al), dtype=self.dtype, device=device)
+            self.off = 0
+        out = self.buf[self.off:self.off + n]
+        self.off += n_al
+        self.used += n_al
+        return out
+
+
+zeros_f64 = ZeroArena(torch.float64, 1 << 14)
+zeros_f32 = ZeroArena(torch.float32, 1 << 16)
+
+
+def new_batch():
+    """Marks a batch boundary for the scratch arenas (called by CoordinateManager.__init__)."""
+    zeros_f64.new_period()
+    zeros_f32.new_period()
 
 
 def _ptr(t):
@@ -218,6 +260,12 @@ def pack_weights(w: torch.Tensor, transpose: bool, mirror: bool) -> torch.Tensor
     return packed
 
 
+def pack_weights_batched(desc_table_dev: torch.Tensor, n_descs: int, total_blocks: int):
+    """One launch re-packing many kernels; desc_table_dev is a device uint8 tensor of gcd_pack_desc records."""
+    call("gcd_conv_pack_weights_batched", desc_table_dev.data_ptr(), n_descs, total_blocks, _stream())
+    _count()
+
+
 def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=MATH_FP32_SIMT,
                  w_packed=None, stats=None):
     """out[o] = sum_k inp[nbr[k, o]] @ B_k, B_k = w3[k] (or w3[wsel(k)]^T when transpose_w).
@@ -293,33 +341,36 @@ def im2col(inp, nbr, ld_out: int, out_dtype) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------ batch norm
-def bn_forward(x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool, residual=None):
-    """Returns (y, mean, invstd); mean/invstd are the statistics used (batch or running)."""
+def bn_forward(x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool, residual=None,
+               stats=None):
+    """Returns (y, mean, invstd); mean/invstd are the statistics used (batch or running).
+    ``stats``: optional fp64 [2c] per-channel sum / sum of squares already produced by the conv epilogue."""
     _require_cuda(x)
     x = _rowmajor(x)
     n, c = x.shape
     dev = x.device
-    mean = torch.empty(c, dtype=torch.float32, device=dev)
-    invstd = torch.empty(c, dtype=torch.float32, device=dev)
-    scale = torch.empty(c, dtype=torch.float32, device=dev)
-    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    buf = torch.empty((4, c), dtype=torch.float32, device=dev)
+    mean, invstd, scale, shift = buf[0], buf[1], buf[2], buf[3]
     st = _stream()
     if training:
-        stats = torch.zeros(2 * c, dtype=torch.float64, device=dev)
-        call("gcd_bn_stats", _ptr(x), _ld(x), n, c, _dtype_code(x), _ptr(stats), st)
-        call("gcd_bn_finalize", _ptr(stats), n, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum), _ptr(running_mean),
-             _ptr(running_var), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), st)
-        _count(2)
+        if stats is None:
+            stats = zeros_f64.take(2 * c, dev)
+            call("gcd_bn_stats", x.data_ptr(), _ld(x), n, c, _dtype_code(x), stats.data_ptr(), st)
+            _count()
+        call("gcd_bn_finalize", stats.data_ptr(), n, c, gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum),
+             running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), st)
+        _count()
     else:
-        call("gcd_bn_fold_eval", c, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), st)
+        call("gcd_bn_fold_eval", c, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(), float(eps),
+             scale.data_ptr(), shift.data_ptr(), st)
         mean = running_mean
         invstd = torch.rsqrt(running_var + eps)
         _count()
     y = torch.empty_like(x)
     if residual is not None:
         residual = _rowmajor(residual)
-    call("gcd_bn_apply", _ptr(x), _ld(x), n, c, _ptr(scale), _ptr(shift), _ptr(residual), _ld(residual) if residual is not None else 0,
-         int(relu), _ptr(y), _ld(y), _dtype_code(x), st)
+    call("gcd_bn_apply", x.data_ptr(), _ld(x), n, c, scale.data_ptr(), shift.data_ptr(), residual.data_ptr() if residual is not None else None,
+         _ld(residual) if residual is not None else 0, int(relu), y.data_ptr(), _ld(y), _dtype_code(x), st)
     _count()
     return y, mean, invstd
 
@@ -329,17 +380,18 @@ def bn_backward(dy, x, y, mean, invstd, gamma, relu: bool, training: bool, need_
     dy = _rowmajor(dy)
     n, c = x.shape
     dev = x.device
-    sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+    sums = zeros_f64.take(2 * c, dev)
     st = _stream()
-    call("gcd_bn_backward_reduce", _ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(y), _ld(y) if y is not None else 0, n, c, _ptr(mean), _ptr(invstd),
-         int(relu), _dtype_code(x), _ptr(sums), st)
+    yp, ldy = (y.data_ptr(), _ld(y)) if y is not None else (None, 0)
+    call("gcd_bn_backward_reduce", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yp, ldy, n, c, mean.data_ptr(), invstd.data_ptr(),
+         int(relu), _dtype_code(x), sums.data_ptr(), st)
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if need_dres else None
-    dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
-    dbeta = torch.zeros(c, dtype=torch.float32, device=dev)
-    call("gcd_bn_backward_apply", _ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(y), _ld(y) if y is not None else 0, n, c, _ptr(mean), _ptr(invstd),
-         _ptr(gamma), _ptr(sums), int(relu), int(training), _ptr(dx), _ld(dx), _ptr(dres), _ld(dres) if dres is not None else 0,
-         _ptr(dgamma), _ptr(dbeta), _dtype_code(x), st)
+    dgb = zeros_f32.take(2 * c, dev)
+    dgamma, dbeta = dgb[:c], dgb[c:]
+    call("gcd_bn_backward_apply", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yp, ldy, n, c, mean.data_ptr(), invstd.data_ptr(),
+         gamma.data_ptr(), sums.data_ptr(), int(relu), int(training), dx.data_ptr(), _ld(dx), dres.data_ptr() if dres is not None else None,
+         _ld(dres) if dres is not None else 0, dgamma.data_ptr(), dbeta.data_ptr(), _dtype_code(x), st)
     _count(3)
     return dx, dres, dgamma, dbeta
 

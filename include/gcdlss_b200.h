@@ -188,6 +188,17 @@ typedef struct {
 
 int32_t gcd_conv_wgrad(const gcd_wgrad_args* args, void* stream);
 
+/* Re-pack many kernels in one launch (after an optimiser step).  descs: DEVICE array of n_descs
+ * gcd_pack_desc; descriptor i is handled by thread blocks [block_start_i, block_start_{i+1}) of 256
+ * threads, one thread per element of its image; total_blocks = sum of ceil(image elements / 256). */
+typedef struct {
+  const float* w;        /* fp32 kernel [kv, c_in, c_out] */
+  void* dst;             /* bf16 image, gcd_conv_packed_weight_bytes(kv, c_in, c_out) bytes */
+  int32_t kv, c_in, c_out, transpose, mirror;
+  int32_t block_start;
+} gcd_pack_desc;
+int32_t gcd_conv_pack_weights_batched(const void* descs, int32_t n_descs, int32_t total_blocks, void* stream);
+
 /* 1 when (c_in, c_out, kv) can run on the tcgen05 path (both multiples of 16, c_out <= 512, kv <= 27). */
 int32_t gcd_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t kv);
 

@@ -9,7 +9,8 @@ tot = collections.defaultdict(lambda: [0.0, 0])
 for r in rd:
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    name = re.sub(r"\(.*", "", r["Kernel Name"])
+    name = r["Kernel Name"].replace("(anonymous namespace)::", "")
+    name = re.sub(r"\(.*", "", name)
     name = re.sub(r"^void ", "", name)
     name = re.sub(r"<.*", "", name)
     v = float(r["Metric Value"].replace(",", ""))

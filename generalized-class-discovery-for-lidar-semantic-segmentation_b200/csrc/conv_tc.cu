@@ -5,16 +5,23 @@
 //   tile      = 128 output rows x N (<= 256) output channels, fp32 accumulator in TMEM
 //               (two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
 //   iteration = (kernel offset k with at least one hit in the tile) x (64-channel slice of Cin)
-//   warps 0-3 : producers.  Read the tile's column-major neighbour table once into shared
-//               memory, then per iteration gather 128 input rows x 64 bf16 with 16-byte
-//               cp.async (zero fill for missing neighbours) straight into the 128B-swizzled
-//               K-major operand image; one thread fetches the matching pre-packed weight slice
-//               with a single bulk copy on the TMA engine (cp.async.bulk -> mbarrier tx count).
-//   warp 8    : one lane issues tcgen05.mma (M=128, N, K=16) per 16 channels and commits to the
-//               stage's "empty" barrier; after the tile's last iteration it commits to
-//               "tmem_full".
-//   warps 4-7 : epilogue.  tcgen05.ld the accumulator (lane == output row), add bias, convert,
+//   warps 0-7 : producers.  Copy the tile's column-major neighbour table into shared memory (the next
+//               tile's entries are prefetched into registers while the current tile streams), then per
+//               iteration gather 128 input rows x 64 bf16 with 16-byte cp.async (zero fill for missing
+//               neighbours) straight into the 128B-swizzled K-major operand image and hand the stage
+//               over with cp.async.mbarrier.arrive (completion-triggered: producers never wait for
+//               their own copies); one thread fetches the matching pre-packed weight slice with a
+//               single bulk copy on the TMA engine (cp.async.bulk -> mbarrier tx count).
+//   warp 12   : one lane issues tcgen05.mma (M=128, N, K=16) per 16 channels and commits to the
+//               stage's "empty" barrier; after the tile's last iteration it commits to "tmem_full".
+//   warps 8-11: epilogue.  tcgen05.ld the accumulator (lane == output row), add bias, convert,
 //               store the row; then release the accumulator buffer.
+// Every role is a single instruction stream per warp, so the per-iteration instruction count of each
+// role is what bounds the pipeline (measured: ~1100 cycles/iteration before the loops were stripped of
+// integer divisions, index-load -> copy dependency chains and descriptor rebuilds).  Hence: all
+// addresses that do not depend on the neighbour index are precomputed, indices are loaded once per
+// offset, and the MMA lane only adds constants to prebuilt descriptors.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -26,16 +33,20 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                 // bf16 per 128-byte operand row
 constexpr int kRowBytes = 128;
 constexpr int kABytes = kTileM * kRowBytes; // 16 KB
-constexpr int kProducerThreads = 128;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
-constexpr int kTcThreads = kProducerThreads + kEpilogueThreads + 32;
+constexpr int kEpilogueWarp0 = kProducerWarps;        // 8: (8 + i) % 4 == i, the TMEM lane quarter rule
+constexpr int kMmaWarp = kProducerWarps + 4;          // 12
+constexpr int kWeightWarp = kProducerWarps + 5;       // 13: issues the weight bulk copies of the forward kernel
+constexpr int kTcThreads = kProducerThreads + kEpilogueThreads + 64;
 constexpr int kMaxKV = 27;
 constexpr int kMaxStages = 8;
-constexpr int kLag = 2;                     // cp.async groups a producer thread keeps in flight
 constexpr int kTileRing = 16;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM columns between the two accumulator buffers
 constexpr int kSmemBudget = 226 * 1024;
+constexpr int kTableRegs = (kMaxKV + 1) / 2;                    // table entries a producer thread prefetches per tile
 
 struct FwdParams {
   const __nv_bfloat16* in; int64_t ld_in;
@@ -44,7 +55,6 @@ struct FwdParams {
   int n_tile_cols;                 // columns per N tile (<= 256, % 16 == 0)
   int n_tiles_n;
   const uint8_t* w_packed;         // [kv][nq][c_out rows][128 B] swizzled K-major images
-  int mirror;
   const float* bias;
   void* out; int64_t ld_out; int out_is_bf16;
   int stages;
@@ -65,6 +75,10 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
   return L;
 }
 
+// kNQ = number of 64-channel slices of Cin when known at compile time (1, 2, 3, 4, 6), 0 = runtime loop.
+// With kNQ known the slice loop is unrolled and every copy uses an immediate offset from a per-offset base
+// pointer, which is what keeps the producer loop at a few dozen instructions per stage.
+template <int kNQ>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is at least 16-byte aligned; the swizzle pattern needs 1024.
@@ -77,136 +91,193 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
   uint64_t* tmem_full = bars + 2 * kMaxStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* s_tmem_base = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint32_t* s_any = s_tmem_base + 1;            // [4] per-producer-warp offset masks
-  int32_t* s_iters = reinterpret_cast<int32_t*>(s_any + 4);  // [kTileRing]
+  uint32_t* s_any = s_tmem_base + 1;            // [kProducerWarps] per-producer-warp offset masks
+  int32_t* s_iters = reinterpret_cast<int32_t*>(s_any + kProducerWarps);  // [kTileRing]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const int nq = (p.c_in + kChunkK - 1) / kChunkK;
+  const int nq = kNQ ? kNQ : (p.c_in + kChunkK - 1) / kChunkK;
+  const int last_width = p.c_in - (nq - 1) * kChunkK;      // channels of the last slice (multiple of 16)
   const int64_t tiles_m = (p.n_out + kTileM - 1) / kTileM;
   const int64_t n_work = tiles_m * p.n_tiles_n;
+  const uint32_t rot = (blockIdx.x * 11u) % (uint32_t)p.kv;   // per-CTA rotation of the offset order (spreads weight reads)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads); }
+    // full: one completion-triggered arrival per gather thread + the weight warp's arrive.expect_tx
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads + 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_base;
 
-  if (warp < 4) {
-    // ===================================================================== producers
-    const int t = threadIdx.x;                 // 0..127 = row of the tile for the table load
-    const int chunk = lane & 7, rsub = lane >> 3;
-    uint32_t st_issue = 0, ph_issue = 0;       // stage being filled, its parity for the empty barrier
-    uint32_t st_arrive = 0;                    // stage whose completion is signalled next
-    uint32_t in_flight = 0;                    // committed-but-not-signalled groups of this thread
-    uint32_t tile_seq = 0;
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+  // order in which a tile's active offsets are visited (shared by the gather warps and the weight warp)
+  auto rotate = [&](uint32_t mask, uint32_t& hi, uint32_t& lo) {
+    if (mask == 0) mask = 1;                   // degenerate tile: run offset 0 with all-zero rows
+    lo = mask & ((1u << rot) - 1u);
+    hi = mask & ~((1u << rot) - 1u);
+    if (hi == 0) { hi = lo; lo = 0; }
+  };
+
+  if (warp < kProducerWarps) {
+    // ===================================================================== gather producers
+    const int t = threadIdx.x;                 // 0..255
+    const int trow = t & (kTileM - 1);         // tile row this thread loads table entries for
+    const int tpar = t >> 7;                   // ... for offsets k = tpar, tpar + 2, ...
+    const int chunk = lane & 7;
+    const int row0 = warp * 4 + (lane >> 3);   // this thread's rows are row0 + 32 j, j = 0..3
+    const uint32_t doff0 = row0 * kRowBytes + ((chunk ^ (row0 & 7)) << 4);   // + 4096 j for the other rows
+    const char* col_base = reinterpret_cast<const char*>(p.in + chunk * 8);
+    const int64_t ld_bytes = p.ld_in * 2;
+    const bool last_active = chunk * 8 < last_width;
+    const uint32_t a_base = smem_u32(smem + L.a_off) + doff0;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+
+    auto load_table = [&](int64_t work, int (&regs)[kTableRegs]) {
       const int64_t tm = work / p.n_tiles_n;
-      const int tn = (int)(work - tm * p.n_tiles_n);
-      const int64_t row0 = tm * kTileM;
-      named_bar_sync(1, kProducerThreads);     // previous tile's table no longer needed by anyone
-      uint32_t my_mask = 0;
-      {
-        const int64_t r = row0 + t;
-        for (int k = 0; k < p.kv; ++k) {
-          int idx = -1;
-          if (r < p.n_out) idx = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.n_out + r]) : (int)r;
-          s_nbr[k * kTileM + t] = idx;
-          if (__any_sync(0xffffffffu, idx >= 0)) my_mask |= 1u << k;
-        }
-        if (lane == 0) s_any[warp] = my_mask;
+      const int64_t r = tm * kTileM + trow;
+#pragma unroll
+      for (int i = 0; i < kTableRegs; ++i) {
+        const int k = 2 * i + tpar;
+        int v = -1;
+        if (k < p.kv && r < p.n_out) v = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.n_out + r]) : (int)r;
+        regs[i] = v;
       }
-      named_bar_sync(1, kProducerThreads);
-      uint32_t mask = s_any[0] | s_any[1] | s_any[2] | s_any[3];
-      if (mask == 0) mask = 1;                 // degenerate tile: run offset 0 with all-zero rows
-      if (t == 0) s_iters[tile_seq & (kTileRing - 1)] = __popc(mask) * nq;
+    };
+
+    uint32_t st = 0, ph = 0;                   // stage being filled, parity of its empty barrier
+    uint32_t tile_seq = 0;
+    int table[kTableRegs];
+    if ((int64_t)blockIdx.x < n_work) load_table(blockIdx.x, table);
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+      named_bar_sync(1, kProducerThreads + 32);  // previous tile's table no longer needed by anyone (weight warp included)
+      uint32_t my_mask = 0;
+#pragma unroll
+      for (int i = 0; i < kTableRegs; ++i) {
+        const int k = 2 * i + tpar;
+        if (k < p.kv) {
+          s_nbr[k * kTileM + trow] = table[i];
+          if (__any_sync(0xffffffffu, table[i] >= 0)) my_mask |= 1u << k;
+        }
+      }
+      if (lane == 0) s_any[warp] = my_mask;
+      named_bar_sync(1, kProducerThreads + 32);
+      if (work + gridDim.x < n_work) load_table(work + gridDim.x, table);   // prefetch: consumed at the next tile start
+      uint32_t mask = 0, lo_mask;
+#pragma unroll
+      for (int w = 0; w < kProducerWarps; ++w) mask |= s_any[w];
+      if (t == 0) s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
+      rotate(mask, mask, lo_mask);
 
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int wk = p.mirror ? p.kv - 1 - k : k;
-        for (int q = 0; q < nq; ++q) {
-          mbar_wait(&empty_bar[st_issue], ph_issue ^ 1);
-          const int width = min(kChunkK, p.c_in - q * kChunkK);   // channels in this slice (multiple of 16)
-          if (t == 0) {
-            const uint32_t bytes = (uint32_t)p.n_tile_cols * kRowBytes;
-            const uint8_t* src = p.w_packed + ((int64_t)(wk * nq + q) * p.c_out + (int64_t)tn * p.n_tile_cols) * kRowBytes;
-            mbar_expect_tx(&full_bar[st_issue], bytes);
-            bulk_g2s(smem_u32(smem + L.b_off + st_issue * L.b_bytes), src, bytes, &full_bar[st_issue]);
-          }
-          const uint32_t a_stage = smem_u32(smem + L.a_off + st_issue * kABytes);
-          if (chunk * 8 < width) {
+        if (mask == 0) { mask = lo_mask; lo_mask = 0; }
+        const int* nb = s_nbr + k * kTileM + row0;
+        const int i0 = nb[0], i1 = nb[32], i2 = nb[64], i3 = nb[96];
+        const char* s0 = col_base + (int64_t)max(i0, 0) * ld_bytes;
+        const char* s1 = col_base + (int64_t)max(i1, 0) * ld_bytes;
+        const char* s2 = col_base + (int64_t)max(i2, 0) * ld_bytes;
+        const char* s3 = col_base + (int64_t)max(i3, 0) * ld_bytes;
+        const uint32_t n0 = i0 >= 0 ? 16u : 0u, n1 = i1 >= 0 ? 16u : 0u, n2 = i2 >= 0 ? 16u : 0u, n3 = i3 >= 0 ? 16u : 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int r = j * 16 + warp * 4 + rsub;
-              const int idx = s_nbr[k * kTileM + r];
-              const __nv_bfloat16* src = p.in + (int64_t)(idx >= 0 ? idx : 0) * p.ld_in + q * kChunkK + chunk * 8;
-              cp_async_16(a_stage + r * kRowBytes + ((chunk ^ (r & 7)) << 4), src, idx >= 0 ? 16u : 0u);
-            }
+        for (int q = 0; q < (kNQ ? kNQ : 8); ++q) {
+          if (!kNQ && q >= nq) break;
+          mbar_wait_addr(empty0 + st * 8, ph ^ 1);
+          if (q + 1 < nq || last_active) {
+            const uint32_t a_stage = a_base + st * kABytes;
+            cp_async_16(a_stage, s0 + q * (kChunkK * 2), n0);
+            cp_async_16(a_stage + 4096, s1 + q * (kChunkK * 2), n1);
+            cp_async_16(a_stage + 8192, s2 + q * (kChunkK * 2), n2);
+            cp_async_16(a_stage + 12288, s3 + q * (kChunkK * 2), n3);
           }
-          cp_async_commit();
-          ++in_flight;
-          if (++st_issue == (uint32_t)S) { st_issue = 0; ph_issue ^= 1; }
-          if (in_flight > kLag) {
-            cp_async_wait<kLag>();
-            fence_proxy_async();
-            mbar_arrive(&full_bar[st_arrive]);
-            if (++st_arrive == (uint32_t)S) st_arrive = 0;
-            --in_flight;
-          }
-        }
-      }
-    }
-    // drain
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (in_flight) {
-      mbar_arrive(&full_bar[st_arrive]);
-      if (++st_arrive == (uint32_t)S) st_arrive = 0;
-      --in_flight;
-    }
-  } else if (warp == 8) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16((uint32_t)p.n_tile_cols, 0, 0);
-      uint32_t st = 0, ph = 0, tile_seq = 0;
-      for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
-        const uint32_t buf = tile_seq & 1;
-        mbar_wait(&tmem_empty[buf], ((tile_seq >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * kAccStride;
-        int n_iters = 1;
-        for (int it = 0; it < n_iters; ++it) {
-          mbar_wait(&full_bar[st], ph);
-          tc_fence_after();
-          if (it == 0) n_iters = s_iters[tile_seq & (kTileRing - 1)];
-          const int q = it % nq;
-          const int ksteps = min(kChunkK, p.c_in - q * kChunkK) / 16;
-          const uint64_t da = make_smem_desc_sw128(smem_u32(smem + L.a_off + st * kABytes), 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(smem_u32(smem + L.b_off + st * L.b_bytes), 16, 1024);
-          for (int ks = 0; ks < ksteps; ++ks)
-            mma_bf16_ss(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (it | ks) != 0);
-          mma_commit(&empty_bar[st]);
+          cp_async_mbar_arrive_noinc_addr(full0 + st * 8);   // arrives when this thread's copies have landed
           if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
         }
-        mma_commit(&tmem_full[buf]);
       }
     }
-    __syncwarp();
+    cp_async_wait_all();                                 // nothing may still be writing smem at exit
+  } else if (warp == kWeightWarp) {
+    // ===================================================================== weight producer (TMA bulk copies)
+    // Walks the same (tile, offset, slice) sequence as the gather warps and, per stage, posts the transaction
+    // count and one bulk copy of the pre-packed [n_tile_cols x 64] weight image.
+    const bool leader = elect_one();
+    const uint32_t b_base = smem_u32(smem + L.b_off);
+    const uint32_t b_bytes = L.b_bytes;
+    uint32_t st = 0, ph = 0;
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+      const int tn = (int)(work % p.n_tiles_n);
+      named_bar_sync(1, kProducerThreads + 32);
+      named_bar_sync(1, kProducerThreads + 32);
+      uint32_t mask = 0, lo_mask;
+#pragma unroll
+      for (int w = 0; w < kProducerWarps; ++w) mask |= s_any[w];
+      rotate(mask, mask, lo_mask);
+      const uint8_t* w_tile = p.w_packed + (int64_t)tn * p.n_tile_cols * kRowBytes;
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (mask == 0) { mask = lo_mask; lo_mask = 0; }
+        const uint8_t* w_k = w_tile + (int64_t)k * nq * p.c_out * kRowBytes;
+        for (int q = 0; q < nq; ++q) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[st], b_bytes);
+            bulk_g2s(b_base + st * b_bytes, w_k + (int64_t)q * p.c_out * kRowBytes, b_bytes, &full_bar[st]);
+          }
+          __syncwarp();
+          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================================================== MMA issuer
+    // The whole warp runs the loop with warp-uniform values (so descriptors live in uniform registers and there is
+    // no divergence bookkeeping around every instruction); one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = make_idesc_bf16((uint32_t)p.n_tile_cols, 0, 0);
+    const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem + L.a_off), 16, 1024);
+    const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem + L.b_off), 16, 1024);
+    const uint64_t da_step = kABytes >> 4, db_step = L.b_bytes >> 4;      // descriptor address units are 16 bytes
+    const int last_ksteps = last_width / 16;
+    const bool leader = elect_one();
+    uint32_t st = 0, ph = 0, tile_seq = 0;
+    uint64_t da = da0, db = db0;
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+      const uint32_t buf = tile_seq & 1;
+      mbar_wait(&tmem_empty[buf], ((tile_seq >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * kAccStride;
+      int n_iters = 1, q = 0;
+      uint32_t accumulate = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        if (it == 0) n_iters = s_iters[tile_seq & (kTileRing - 1)];
+        const int ksteps = (q == nq - 1) ? last_ksteps : kChunkK / 16;
+        if (leader) {
+          for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)ks);
+          mma_commit(&empty_bar[st]);
+        }
+        accumulate = 1;
+        __syncwarp();
+        if (++q == nq) q = 0;
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0; db = db0; } else { da += da_step; db += db_step; }
+      }
+      if (leader) mma_commit(&tmem_full[buf]);
+      __syncwarp();
+    }
   } else {
     // ===================================================================== epilogue
-    const int ew = warp - 4;                   // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = warp - kEpilogueWarp0;      // == warp % 4: the TMEM lane quarter this warp may read
     uint32_t tile_seq = 0;
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
       const int64_t tm = work / p.n_tiles_n;
       const int tn = (int)(work - tm * p.n_tiles_n);
       const uint32_t buf = tile_seq & 1;
-      mbar_wait(&tmem_full[buf], (tile_seq >> 1) & 1);
+      mbar_wait_warp(&tmem_full[buf], (tile_seq >> 1) & 1, 128);
       tc_fence_after();
       const int64_t row = tm * kTileM + ew * 32 + lane;
       const int col0 = tn * p.n_tile_cols;
@@ -237,25 +308,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------ weight packing
 // Image of (offset k, 64-channel slice q): rows = output channel n (c_out of them), 128 B per row,
 // element (n, kk) at n*128 + (((kk>>3) ^ (n&7))<<4) + (kk&7)*2; value = B_k[q*64+kk][n].
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int kv, int c_in, int c_out, int transpose,
-                                                            int mirror, __nv_bfloat16* __restrict__ packed) {
+__device__ __forceinline__ void pack_one(const float* __restrict__ w, int kv, int c_in, int c_out, int transpose, int mirror,
+                                         __nv_bfloat16* __restrict__ packed, int64_t t) {
   // logical operand: K' x N' where (K', N') = (c_in, c_out) for forward, (c_out, c_in) for dgrad
   const int kdim = transpose ? c_out : c_in, ndim = transpose ? c_in : c_out;
   const int nq = (kdim + kChunkK - 1) / kChunkK;
   const int64_t total = (int64_t)kv * nq * ndim * kChunkK;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int kk = (int)(t % kChunkK);
   const int n = (int)((t / kChunkK) % ndim);
@@ -268,8 +339,12 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     v = transpose ? w[((int64_t)ksrc * c_in + n) * c_out + c] : w[((int64_t)ksrc * c_in + c) * c_out + n];
   }
   const int64_t img = ((int64_t)k * nq + q) * ndim * kChunkK;  // elements
-  const int64_t off = img + (int64_t)n * kChunkK + ((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7));
-  packed[off] = __float2bfloat16_rn(v);
+  packed[img + (int64_t)n * kChunkK + ((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7))] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int kv, int c_in, int c_out, int transpose,
+                                                            int mirror, __nv_bfloat16* __restrict__ packed) {
+  pack_one(w, kv, c_in, c_out, transpose, mirror, packed, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // All kernels of a model in one launch: block b works on descriptor d with block_start[d] <= b < block_start[d+1].
@@ -286,26 +361,8 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackDes
     if (descs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const PackDesc d = descs[lo];
-  const int kdim = d.transpose ? d.c_out : d.c_in, ndim = d.transpose ? d.c_in : d.c_out;
-  const int nq = (kdim + kChunkK - 1) / kChunkK;
-  const int64_t total = (int64_t)d.kv * nq * ndim * kChunkK;
-  const int64_t t = (int64_t)(blockIdx.x - d.block_start) * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int kk = (int)(t % kChunkK);
-  const int n = (int)((t / kChunkK) % ndim);
-  const int q = (int)((t / ((int64_t)kChunkK * ndim)) % nq);
-  const int k = (int)(t / ((int64_t)kChunkK * ndim * nq));
-  const int c = q * kChunkK + kk;
-  float v = 0.f;
-  if (c < kdim) {
-    const int ksrc = (d.transpose && d.mirror) ? d.kv - 1 - k : k;
-    v = d.transpose ? d.w[((int64_t)ksrc * d.c_in + n) * d.c_out + c] : d.w[((int64_t)ksrc * d.c_in + c) * d.c_out + n];
-  }
-  const int64_t img = ((int64_t)k * nq + q) * ndim * kChunkK;
-  d.dst[img + (int64_t)n * kChunkK + ((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7))] = __float2bfloat16_rn(v);
+  pack_one(d.w, d.kv, d.c_in, d.c_out, d.transpose, d.mirror, d.dst, (int64_t)(blockIdx.x - d.block_start) * blockDim.x + threadIdx.x);
 }
-}  // namespace
-
 
 // ======================================================================================= wgrad
 // dW[k] (Cin x Cout, fp32) += A_k^T G_k over the pairs of offset k.  Work item = (offset k, chunk of
@@ -315,10 +372,10 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackDes
 //   D[128 (Cin slice) x Cout] += A^T[128 x 16 pairs] * G[16 pairs x Cout]   (4 MMAs per stage)
 // Rows of A^T beyond Cin read stale shared memory; they only produce accumulator lanes that the
 // epilogue never reads.  The epilogue adds the accumulator into dW with fp32 atomics.
-namespace {
 constexpr int kWgPairs = 64;                         // pairs (MMA K) per stage
 constexpr int kSlabBytes = kWgPairs * kRowBytes;     // 8 KB: 64 rows x 64 channels
 constexpr int kWgMaxOffsets = 128;
+constexpr int kWgRowsPerThread = kWgPairs * 8 / kProducerThreads;   // 2
 
 struct WgParams {
   const __nv_bfloat16* in; int64_t ld_in;
@@ -350,7 +407,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     fence_mbar_init();
     int cum = 0;
     for (int k = 0; k < p.kv; ++k) {
@@ -360,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
     }
     s_cum[p.kv] = cum;
   }
-  if (warp == 8) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -379,64 +436,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
     p_end = min(p_begin + (int64_t)p.chunk, end_k);
   };
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ===================================================================== producers
-    const int chunk16 = lane & 7, rsub = lane >> 3;
-    uint32_t st_issue = 0, ph_issue = 0, st_arrive = 0, in_flight = 0;
+    const int chunk16 = lane & 7;
+    int rows[kWgRowsPerThread];
+    uint32_t doff[kWgRowsPerThread];
+#pragma unroll
+    for (int j = 0; j < kWgRowsPerThread; ++j) {
+      rows[j] = j * 32 + warp * 4 + (lane >> 3);
+      doff[j] = rows[j] * kRowBytes + ((chunk16 ^ (rows[j] & 7)) << 4);
+    }
+    const int64_t lda = p.ld_in * 2, ldg = p.ld_g * 2;                       // bytes
+    const uint32_t stage0 = smem_u32(smem);
+    uint32_t st = 0, ph = 0;
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
       int k, mt; int64_t p_begin, p_end;
       decode(work, k, p_begin, p_end, mt);
       const int c_base = mt * 128;
-      for (int64_t p0 = p_begin; p0 < p_end; p0 += kWgPairs) {
-        int ri[4], ro[4];
+      const char* a_col = reinterpret_cast<const char*>(p.in + c_base + chunk16 * 8);
+      const char* g_col = reinterpret_cast<const char*>(p.gout + chunk16 * 8);
+      const bool a_on0 = c_base + chunk16 * 8 < p.c_in, a_on1 = c_base + 64 + chunk16 * 8 < p.c_in;
+      // software pipeline: the pair indices of the next stage are fetched while this stage's copies are issued
+      int ri[kWgRowsPerThread], ro[kWgRowsPerThread];
+      auto fetch = [&](int64_t p0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t pp = p0 + j * 16 + warp * 4 + rsub;
+        for (int j = 0; j < kWgRowsPerThread; ++j) {
+          const int64_t pp = p0 + rows[j];
           if (pp < p_end) {
             ri[j] = p.pair_in ? __ldg(&p.pair_in[pp]) : (int)pp;
             ro[j] = p.pair_out ? __ldg(&p.pair_out[pp]) : (int)pp;
           } else { ri[j] = -1; ro[j] = -1; }
         }
-        mbar_wait(&empty_bar[st_issue], ph_issue ^ 1);
-        const uint32_t a_stage = smem_u32(smem + st_issue * stage_bytes);
+      };
+      fetch(p_begin);
+      for (int64_t p0 = p_begin; p0 < p_end; p0 += kWgPairs) {
+        const char* sa[kWgRowsPerThread]; const char* sg[kWgRowsPerThread]; uint32_t nb[kWgRowsPerThread];
+#pragma unroll
+        for (int j = 0; j < kWgRowsPerThread; ++j) {
+          sa[j] = a_col + (int64_t)(ri[j] >= 0 ? ri[j] : 0) * lda;
+          sg[j] = g_col + (int64_t)(ro[j] >= 0 ? ro[j] : 0) * ldg;
+          nb[j] = ri[j] >= 0 ? 16u : 0u;
+        }
+        if (p0 + kWgPairs < p_end) fetch(p0 + kWgPairs);
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        const uint32_t a_stage = stage0 + st * stage_bytes;
         const uint32_t g_stage = a_stage + 2 * kSlabBytes;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = j * 16 + warp * 4 + rsub;
-          const uint32_t row_off = r * kRowBytes + ((chunk16 ^ (r & 7)) << 4);
-          const __nv_bfloat16* src_a = p.in + (int64_t)(ri[j] >= 0 ? ri[j] : 0) * p.ld_in + c_base + chunk16 * 8;
-          const __nv_bfloat16* src_g = p.gout + (int64_t)(ro[j] >= 0 ? ro[j] : 0) * p.ld_g + chunk16 * 8;
-          const uint32_t nb = ri[j] >= 0 ? 16u : 0u;
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            if (c_base + s * 64 + chunk16 * 8 < p.c_in) cp_async_16(a_stage + s * kSlabBytes + row_off, src_a + s * 64, nb);
+        for (int j = 0; j < kWgRowsPerThread; ++j) {
+          if (a_on0) cp_async_16(a_stage + doff[j], sa[j], nb[j]);
+          if (a_on1) cp_async_16(a_stage + kSlabBytes + doff[j], sa[j] + 128, nb[j]);
           for (int s = 0; s < p.g_slabs; ++s)
-            if (s * 64 + chunk16 * 8 < p.c_out) cp_async_16(g_stage + s * kSlabBytes + row_off, src_g + s * 64, nb);
+            if (s * 64 + chunk16 * 8 < p.c_out) cp_async_16(g_stage + s * kSlabBytes + doff[j], sg[j] + s * 128, nb[j]);
         }
-        cp_async_commit();
-        ++in_flight;
-        if (++st_issue == (uint32_t)S) { st_issue = 0; ph_issue ^= 1; }
-        if (in_flight > kLag) {
-          cp_async_wait<kLag>();
-          fence_proxy_async();
-          mbar_arrive(&full_bar[st_arrive]);
-          if (++st_arrive == (uint32_t)S) st_arrive = 0;
-          --in_flight;
-        }
+        cp_async_mbar_arrive_noinc(&full_bar[st]);
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (in_flight) {
-      mbar_arrive(&full_bar[st_arrive]);
-      if (++st_arrive == (uint32_t)S) st_arrive = 0;
-      --in_flight;
-    }
-  } else if (warp == 8) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    cp_async_wait_all();
+  } else if (warp == kMmaWarp) {
+    // ===================================================================== MMA issuer (warp-uniform, elected lane issues)
+    {
       const uint32_t idesc = make_idesc_bf16((uint32_t)p.c_out, 1, 1);   // both operands MN-major
+      const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem), kSlabBytes, 1024);
+      const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem) + 2 * kSlabBytes, kSlabBytes, 1024);
+      const uint64_t stage_step = stage_bytes >> 4, k_step = (16 * kRowBytes) >> 4;
+      const bool leader = elect_one();
       uint32_t st = 0, ph = 0, seq = 0;
+      uint64_t da = da0, db = db0;
       for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++seq) {
         int k, mt; int64_t p_begin, p_end;
         decode(work, k, p_begin, p_end, mt);
@@ -445,32 +511,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kAccStride;
         const int n_stages = (int)((p_end - p_begin + kWgPairs - 1) / kWgPairs);
+        uint32_t accumulate = 0;
         for (int it = 0; it < n_stages; ++it) {
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + st * stage_bytes);
-          const uint32_t g_addr = a_addr + 2 * kSlabBytes;
-          for (int ks = 0; ks < kWgPairs / 16; ++ks) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + ks * 16 * kRowBytes, kSlabBytes, 1024);
-            const uint64_t db = make_smem_desc_sw128(g_addr + ks * 16 * kRowBytes, kSlabBytes, 1024);
-            mma_bf16_ss(tmem_d, da, db, idesc, (it | ks) != 0);
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < kWgPairs / 16; ++ks) mma_bf16_ss(tmem_d, da + ks * k_step, db + ks * k_step, idesc, accumulate | (uint32_t)ks);
+            mma_commit(&empty_bar[st]);
           }
-          mma_commit(&empty_bar[st]);
-          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
+          accumulate = 1;
+          __syncwarp();
+          if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0; db = db0; } else { da += stage_step; db += stage_step; }
         }
-        mma_commit(&tmem_full[buf]);
+        if (leader) mma_commit(&tmem_full[buf]);
+        __syncwarp();
       }
     }
-    __syncwarp();
-  } else {
-    // ===================================================================== epilogue
-    const int ew = warp - 4;
+  } else if (warp < kMmaWarp) {
+    // ===================================================================== epilogue (warps 8-11; warp 13 idles here)
+    const int ew = warp - kEpilogueWarp0;
     uint32_t seq = 0;
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++seq) {
       int k, mt; int64_t p_begin, p_end;
       decode(work, k, p_begin, p_end, mt);
       const uint32_t buf = seq & 1;
-      mbar_wait(&tmem_full[buf], (seq >> 1) & 1);
+      mbar_wait_warp(&tmem_full[buf], (seq >> 1) & 1, 128);
       tc_fence_after();
       const int c = mt * 128 + ew * 32 + lane;          // input channel = accumulator lane
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)(ew * 32) << 16);
@@ -485,13 +551,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 }  // namespace
 
@@ -516,7 +583,7 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   p.chunk = (int)chunk;
   const int stage_bytes = (2 + p.g_slabs) * kSlabBytes;
   int stages = std::min(kMaxStages, (kSmemBudget - 1024 - 1024) / stage_bytes);
-  if (stages <= kLag) { set_error("conv_wgrad_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
+  if (stages < 2) { set_error("conv_wgrad_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 1024;
   static bool attr_set = false;
@@ -546,24 +613,39 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.n_tiles_n = (a->c_out + 255) / 256;
   p.n_tile_cols = a->c_out / p.n_tiles_n;
   if (p.n_tile_cols % 16 != 0 || p.n_tile_cols * p.n_tiles_n != a->c_out) { set_error("conv_forward_tc: cannot split %d output channels into equal tiles", a->c_out); return GCD_ERR_UNSUPPORTED; }
-  p.w_packed = (const uint8_t*)a->w_packed; p.mirror = 0;  // mirroring is baked into the packed image
+  p.w_packed = (const uint8_t*)a->w_packed;  // offset mirroring (dgrad of stride-1 maps) is baked into the packed image
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
   int stages = (kSmemBudget - 1024 - kMaxKV * kTileM * 4 - 512) / stage_bytes;
-  stages = std::max(2, std::min(stages, kMaxStages));
-  if (stages <= kLag) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
+  stages = std::min(stages, kMaxStages);
+  if (const char* e = getenv("GCD_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));   // tuning aid
+  if (stages < 2) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;
+  using Kernel = void (*)(const FwdParams);
+  Kernel kernel;
+  switch ((a->c_in + kChunkK - 1) / kChunkK) {
+    case 1: kernel = conv_fwd_tc_kernel<1>; break;
+    case 2: kernel = conv_fwd_tc_kernel<2>; break;
+    case 3: kernel = conv_fwd_tc_kernel<3>; break;
+    case 4: kernel = conv_fwd_tc_kernel<4>; break;
+    case 6: kernel = conv_fwd_tc_kernel<6>; break;
+    default: kernel = conv_fwd_tc_kernel<0>; break;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_fwd_tc_kernel)");
+    for (Kernel k : {(Kernel)conv_fwd_tc_kernel<0>, (Kernel)conv_fwd_tc_kernel<1>, (Kernel)conv_fwd_tc_kernel<2>, (Kernel)conv_fwd_tc_kernel<3>,
+                     (Kernel)conv_fwd_tc_kernel<4>, (Kernel)conv_fwd_tc_kernel<6>}) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_fwd_tc_kernel)");
+    }
     attr_set = true;
   }
+  if (a->c_in > 8 * kChunkK) { set_error("conv_forward_tc: more than 512 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;
   const unsigned grid = (unsigned)std::min<int64_t>(n_work, kNumSMs);
-  conv_fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  kernel<<<grid, kTcThreads, smem, st>>>(p);
   GCD_LAUNCH_CHECK("gcd_conv_forward(tcgen05)");
   return GCD_OK;
 }

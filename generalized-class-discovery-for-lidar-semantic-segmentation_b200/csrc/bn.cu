@@ -131,6 +131,67 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
   }
 }
 
+// Training-mode normalise in one pass: every thread derives scale/shift for its four channels from the fp64 batch
+// sums (cheap next to the memory traffic), block 0 also publishes mean / invstd for the backward pass and updates the
+// running statistics, so no separate "finalise" launch is needed.
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256) bn_apply_train_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
+                                                              const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, float momentum,
+                                                              float* running_mean, float* running_var, float* __restrict__ mean_out,
+                                                              float* __restrict__ invstd_out, const T* __restrict__ res, int64_t ld_res,
+                                                              int relu, T* __restrict__ y, int64_t ld_y) {
+  const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
+  if (blockIdx.x == 0) {
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const double m = stats[ch] * inv_n;
+      double var = stats[c + ch] * inv_n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean_out[ch] = (float)m;
+      invstd_out[ch] = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean) {
+        const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+      }
+    }
+  }
+  const int groups = (c + 3) / 4;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * groups) return;
+  const int64_t r = t / groups;
+  const int ch = (int)(t - r * groups) * 4;
+  float v[4], rs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (kVec) {
+    Vec4<T>::load(x + r * ld_x + ch, v);
+    if (res) Vec4<T>::load(res + r * ld_res + ch, rs);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = ch + j < c ? to_f32<T>(x[r * ld_x + ch + j]) : 0.f;
+      if (res && ch + j < c) rs[j] = to_f32<T>(res[r * ld_res + ch + j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (ch + j < c) {
+      const double m = stats[ch + j] * inv_n;
+      double var = stats[c + ch + j] * inv_n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = (float)(1.0 / sqrt(var + (double)eps));
+      const float g = gamma ? gamma[ch + j] : 1.f, b = beta ? beta[ch + j] : 0.f;
+      const float scale = g * is, shift = b - (float)m * scale;
+      const float o = fmaf(v[j], scale, shift) + rs[j];
+      v[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+  }
+  if (kVec) Vec4<T>::store(y + r * ld_y + ch, v);
+  else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (ch + j < c) y[r * ld_y + ch + j] = from_f32<T>(v[j]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRedX* kRedY) bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
                                                                      const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
@@ -149,7 +210,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                             const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
-                                                            int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres, int64_t ld_dres) {
+                                                            int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres, int64_t ld_dres,
+                                                            float* dgamma, float* dbeta) {
+  if (blockIdx.x == 0) {                              // parameter gradients: dbeta = sum g, dgamma = sum g * xhat (accumulated)
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      if (dbeta) dbeta[ch] += (float)sums[ch];
+      if (dgamma) dgamma[ch] += (float)sums[c + ch];
+    }
+  }
   const int groups = (c + 3) / 4;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * groups) return;
@@ -275,6 +343,30 @@ extern "C" int32_t gcd_bn_apply(const void* x, int64_t ld_x, int64_t n, int32_t 
   return GCD_OK;
 }
 
+extern "C" int32_t gcd_bn_apply_train(const void* x, int64_t ld_x, int64_t n, int32_t c, const double* stats, const float* gamma,
+                                      const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                      float* mean, float* invstd, const void* residual, int64_t ld_res, int32_t relu, void* y,
+                                      int64_t ld_y, int32_t dtype, void* stream) {
+  GCD_REQUIRE(stats && mean && invstd && c >= 1, "gcd_bn_apply_train: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(n * ((c + 3) / 4), 256));
+  if (dtype == GCD_F32) {
+    using T = float;
+    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
+      bn_apply_train_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+    else
+      bn_apply_train_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+  } else {
+    using T = __nv_bfloat16;
+    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
+      bn_apply_train_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+    else
+      bn_apply_train_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
+  }
+  GCD_LAUNCH_CHECK("gcd_bn_apply_train");
+  return GCD_OK;
+}
+
 extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
                                           int64_t n, int32_t c, const float* mean, const float* invstd, int32_t relu, int32_t dtype,
                                           double* sums, void* stream) {
@@ -299,18 +391,18 @@ extern "C" int32_t gcd_bn_backward_apply(const void* dy, int64_t ld_dy, const vo
     if (dtype == GCD_F32) {
       using T = float;
       if (vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}))
-        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
       else
-        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
     } else {
       using T = __nv_bfloat16;
       if (vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}))
-        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
       else
-        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres);
+        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
     }
   }
-  if (dgamma || dbeta) bn_param_grad_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(sums, c, dgamma, dbeta);
+  if (n <= 0 && (dgamma || dbeta)) bn_param_grad_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(sums, c, dgamma, dbeta);
   GCD_LAUNCH_CHECK("gcd_bn_backward_apply");
   return GCD_OK;
 }

@@ -375,7 +375,6 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackDes
 constexpr int kWgPairs = 64;                         // pairs (MMA K) per stage
 constexpr int kSlabBytes = kWgPairs * kRowBytes;     // 8 KB: 64 rows x 64 channels
 constexpr int kWgMaxOffsets = 128;
-constexpr int kWgRowsPerThread = kWgPairs * 8 / kProducerThreads;   // 2
 
 struct WgParams {
   const __nv_bfloat16* in; int64_t ld_in;
@@ -390,11 +389,12 @@ struct WgParams {
   int stages;
 };
 
+template <int kGS>   // kGS = number of 64-channel slabs of the output gradient (ceil(c_out / 64), 1..4)
 __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
-  const uint32_t stage_bytes = (uint32_t)(2 + p.g_slabs) * kSlabBytes;   // A: 2 slabs, G: g_slabs
+  const uint32_t stage_bytes = (uint32_t)(2 + kGS) * kSlabBytes;         // A: 2 slabs, G: kGS slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)S * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
@@ -439,56 +439,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
   if (warp < kProducerWarps) {
     // ===================================================================== producers
     const int chunk16 = lane & 7;
-    int rows[kWgRowsPerThread];
-    uint32_t doff[kWgRowsPerThread];
-#pragma unroll
-    for (int j = 0; j < kWgRowsPerThread; ++j) {
-      rows[j] = j * 32 + warp * 4 + (lane >> 3);
-      doff[j] = rows[j] * kRowBytes + ((chunk16 ^ (rows[j] & 7)) << 4);
-    }
+    const int row0 = warp * 4 + (lane >> 3);                                 // this thread's pairs of a stage: row0, row0 + 32
+    const uint32_t doff0 = row0 * kRowBytes + ((chunk16 ^ (row0 & 7)) << 4);
     const int64_t lda = p.ld_in * 2, ldg = p.ld_g * 2;                       // bytes
-    const uint32_t stage0 = smem_u32(smem);
+    const uint32_t stage0 = smem_u32(smem) + doff0;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    uint32_t g_on = 0;                                                       // bit s: this thread's chunk exists in gradient slab s
+#pragma unroll
+    for (int s = 0; s < kGS; ++s) g_on |= (s * 64 + chunk16 * 8 < p.c_out ? 1u : 0u) << s;
+    const char* g_col = reinterpret_cast<const char*>(p.gout + chunk16 * 8);
     uint32_t st = 0, ph = 0;
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
       int k, mt; int64_t p_begin, p_end;
       decode(work, k, p_begin, p_end, mt);
       const int c_base = mt * 128;
       const char* a_col = reinterpret_cast<const char*>(p.in + c_base + chunk16 * 8);
-      const char* g_col = reinterpret_cast<const char*>(p.gout + chunk16 * 8);
       const bool a_on0 = c_base + chunk16 * 8 < p.c_in, a_on1 = c_base + 64 + chunk16 * 8 < p.c_in;
       // software pipeline: the pair indices of the next stage are fetched while this stage's copies are issued
-      int ri[kWgRowsPerThread], ro[kWgRowsPerThread];
+      int ri0, ri1, ro0, ro1;
       auto fetch = [&](int64_t p0) {
-#pragma unroll
-        for (int j = 0; j < kWgRowsPerThread; ++j) {
-          const int64_t pp = p0 + rows[j];
-          if (pp < p_end) {
-            ri[j] = p.pair_in ? __ldg(&p.pair_in[pp]) : (int)pp;
-            ro[j] = p.pair_out ? __ldg(&p.pair_out[pp]) : (int)pp;
-          } else { ri[j] = -1; ro[j] = -1; }
-        }
+        const int64_t pa = p0 + row0, pb = pa + 32;
+        ri0 = ro0 = ri1 = ro1 = -1;
+        if (pa < p_end) { ri0 = p.pair_in ? __ldg(&p.pair_in[pa]) : (int)pa; ro0 = p.pair_out ? __ldg(&p.pair_out[pa]) : (int)pa; }
+        if (pb < p_end) { ri1 = p.pair_in ? __ldg(&p.pair_in[pb]) : (int)pb; ro1 = p.pair_out ? __ldg(&p.pair_out[pb]) : (int)pb; }
       };
       fetch(p_begin);
       for (int64_t p0 = p_begin; p0 < p_end; p0 += kWgPairs) {
-        const char* sa[kWgRowsPerThread]; const char* sg[kWgRowsPerThread]; uint32_t nb[kWgRowsPerThread];
-#pragma unroll
-        for (int j = 0; j < kWgRowsPerThread; ++j) {
-          sa[j] = a_col + (int64_t)(ri[j] >= 0 ? ri[j] : 0) * lda;
-          sg[j] = g_col + (int64_t)(ro[j] >= 0 ? ro[j] : 0) * ldg;
-          nb[j] = ri[j] >= 0 ? 16u : 0u;
-        }
+        const char* sa0 = a_col + (int64_t)max(ri0, 0) * lda;
+        const char* sa1 = a_col + (int64_t)max(ri1, 0) * lda;
+        const char* sg0 = g_col + (int64_t)max(ro0, 0) * ldg;
+        const char* sg1 = g_col + (int64_t)max(ro1, 0) * ldg;
+        const uint32_t n0 = ri0 >= 0 ? 16u : 0u, n1 = ri1 >= 0 ? 16u : 0u;
         if (p0 + kWgPairs < p_end) fetch(p0 + kWgPairs);
-        mbar_wait(&empty_bar[st], ph ^ 1);
+        mbar_wait_addr(empty0 + st * 8, ph ^ 1);
         const uint32_t a_stage = stage0 + st * stage_bytes;
-        const uint32_t g_stage = a_stage + 2 * kSlabBytes;
+        if (a_on0) { cp_async_16(a_stage, sa0, n0); cp_async_16(a_stage + 4096, sa1, n1); }
+        if (a_on1) { cp_async_16(a_stage + kSlabBytes, sa0 + 128, n0); cp_async_16(a_stage + kSlabBytes + 4096, sa1 + 128, n1); }
 #pragma unroll
-        for (int j = 0; j < kWgRowsPerThread; ++j) {
-          if (a_on0) cp_async_16(a_stage + doff[j], sa[j], nb[j]);
-          if (a_on1) cp_async_16(a_stage + kSlabBytes + doff[j], sa[j] + 128, nb[j]);
-          for (int s = 0; s < p.g_slabs; ++s)
-            if (s * 64 + chunk16 * 8 < p.c_out) cp_async_16(g_stage + s * kSlabBytes + doff[j], sg[j] + s * 128, nb[j]);
-        }
-        cp_async_mbar_arrive_noinc(&full_bar[st]);
+        for (int s = 0; s < kGS; ++s)
+          if (g_on & (1u << s)) {
+            cp_async_16(a_stage + (2 + s) * kSlabBytes, sg0 + s * 128, n0);
+            cp_async_16(a_stage + (2 + s) * kSlabBytes + 4096, sg1 + s * 128, n1);
+          }
+        cp_async_mbar_arrive_noinc_addr(full0 + st * 8);
         if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
     }
@@ -586,15 +579,19 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   if (stages < 2) { set_error("conv_wgrad_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 1024;
+  using Kernel = void (*)(const WgParams);
+  static const Kernel kernels[4] = {conv_wgrad_tc_kernel<1>, conv_wgrad_tc_kernel<2>, conv_wgrad_tc_kernel<3>, conv_wgrad_tc_kernel<4>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_wgrad_tc_kernel)");
+    for (Kernel k : kernels) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_wgrad_tc_kernel)");
+    }
     attr_set = true;
   }
   const int64_t work_bound = (ceil_div(a->n_pairs, chunk) + a->kv) * p.m_tiles;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(work_bound, kNumSMs));
-  conv_wgrad_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  kernels[p.g_slabs - 1]<<<grid, kTcThreads, smem, st>>>(p);
   GCD_LAUNCH_CHECK("gcd_conv_wgrad(tcgen05)");
   return GCD_OK;
 }

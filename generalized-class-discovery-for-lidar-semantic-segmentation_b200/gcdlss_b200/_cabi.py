@@ -104,6 +104,7 @@ PROTOTYPES = {
     "gcd_im2col": (_i32, [_vp, _i64, _i32, _vp, _i32, _i64, _vp, _i64, _i32, _i32, _vp]),
     "gcd_bn_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "gcd_bn_finalize": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcd_bn_apply_train": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
     "gcd_bn_fold_eval": (_i32, [_i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp]),
     "gcd_bn_apply": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
     "gcd_bn_backward_reduce": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),

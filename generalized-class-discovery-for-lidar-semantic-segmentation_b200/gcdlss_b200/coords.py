@@ -88,6 +88,34 @@ class CoordinateManager:
             self.maps[tensor_stride] = CoordMap(coarse, table, tensor_stride)
         return self.maps[tensor_stride]
 
+    def prebuild_unet(self, n_levels: int = 5, stem_kernel: int = 5, with_pairs: bool = True):
+        """Build everything one MinkUNet forward+backward will ask for (coordinate maps at tensor strides
+        1..2^(n_levels-1), the stem / 3x3x3 / stride-2 / transposed kernel maps and, for training, their pair
+        lists).  Used by the batch prefetcher so the host syncs of the build happen off the training stream."""
+        strides = [1 << l for l in range(n_levels)]
+        for ts in strides:
+            self.get_map(ts)
+        keys = [(1, stem_kernel, 1, False)] + [(ts, 3, 1, False) for ts in strides] + [(ts, 1, 1, False) for ts in strides]
+        keys += [(ts, 2, 2, False) for ts in strides[:-1]] + [(ts, 2, 2, True) for ts in strides[1:]]
+        for key in keys:
+            km = self.kernel_map(*key)
+            if with_pairs and km.nbr is not None and km.kv <= 27:
+                km.pairs
+        return self
+
+    def device_tensors(self):
+        """Every device tensor this manager owns (for cross-stream hand-over)."""
+        out = [self.status]
+        for m in self.maps.values():
+            out += [m.coords, m.table.keys, m.table.vals]
+            out += [t for t in (m.parent, m.code) if t is not None]
+        for km in self._kmaps.values():
+            if km.nbr is not None:
+                out.append(km.nbr)
+            if km._pairs is not None:
+                out += list(km._pairs)
+        return out
+
     # -- kernel maps -----------------------------------------------------------------------
     def kernel_map(self, ts_in: int, kernel_size: int, stride: int, transposed: bool) -> KernelMap:
         key = (ts_in, kernel_size, stride, transposed)

@@ -83,12 +83,18 @@ def _count(n=1):
 
 
 class KernelTimer:
-    """Optional CUDA-event brackets around the convolution launches (bench.py's live roofline).
-    Events are recorded on the launching stream; durations are read after the timed region."""
+    """Optional instrumentation of the convolution launches for bench.py's live roofline.
+
+    ``enabled``: CUDA-event brackets around every launch inside the timed region (on the launching stream).  When the
+    step is host-bound those intervals also contain the idle gap before the launch reaches the GPU, so bench.py
+    additionally uses ``capture``: the launches of one step are remembered (a closure that re-issues the identical
+    call on the same tensors) and replayed back to back after the timed region to measure the kernels alone."""
 
     def __init__(self):
         self.enabled = False
+        self.capture = False
         self.records = []        # (kind, nbr_ptr, n_out, kv, c_in, c_out, start_event, end_event)
+        self.captured = []       # (kind, nbr_ptr, n_out, kv, c_in, c_out, replay_fn)
 
     def bracket(self, kind, nbr, n_out, kv, c_in, c_out):
         if not self.enabled:
@@ -97,6 +103,10 @@ class KernelTimer:
         e0.record()
         self.records.append((kind, nbr.data_ptr() if nbr is not None else 0, n_out, kv, c_in, c_out, e0, e1))
         return e1
+
+    def remember(self, kind, nbr, n_out, kv, c_in, c_out, fn):
+        if self.capture:
+            self.captured.append((kind, nbr.data_ptr() if nbr is not None else 0, n_out, kv, c_in, c_out, fn))
 
 
 kernel_timer = KernelTimer()
@@ -296,10 +306,14 @@ def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, b
     a.in_dtype, a.out_dtype = _dtype_code(inp), _dtype_code(out)
     a.stats = stats.data_ptr() if stats is not None else None
     a.math_mode = math_mode
-    end = kernel_timer.bracket("conv_tc" if math_mode == MATH_BF16_TC else "conv_simt", nbr, n_out, kv, k_dim, n_dim)
+    kind = "conv_tc" if math_mode == MATH_BF16_TC else "conv_simt"
+    end = kernel_timer.bracket(kind, nbr, n_out, kv, k_dim, n_dim)
     call("gcd_conv_forward", C.byref(a), _stream())
     if end is not None:
         end.record()
+    if kernel_timer.capture:
+        keep = (inp, nbr, w3, w_packed, bias, out)        # keeps the operands alive for the replay
+        kernel_timer.remember(kind, nbr, n_out, kv, k_dim, n_dim, lambda a=a, keep=keep: call("gcd_conv_forward", C.byref(a), _stream()))
     _count()
     return out
 
@@ -323,11 +337,15 @@ def conv_wgrad(inp, gout, pairs, kv: int, dw: torch.Tensor, dbias=None, math_mod
     a.n_out = gout.shape[0]
     a.in_dtype, a.gout_dtype = _dtype_code(inp), _dtype_code(gout)
     a.math_mode = math_mode
-    end = kernel_timer.bracket("wgrad_tc" if math_mode == MATH_BF16_TC else "wgrad_simt", pairs[0] if pairs is not None else None,
-                               gout.shape[0], kv, inp.shape[1], gout.shape[1])
+    kind = "wgrad_tc" if math_mode == MATH_BF16_TC else "wgrad_simt"
+    end = kernel_timer.bracket(kind, pairs[0] if pairs is not None else None, gout.shape[0], kv, inp.shape[1], gout.shape[1])
     call("gcd_conv_wgrad", C.byref(a), _stream())
     if end is not None:
         end.record()
+    if kernel_timer.capture:
+        keep = (inp, gout, pairs, dw, dbias)
+        kernel_timer.remember(kind, pairs[0] if pairs is not None else None, gout.shape[0], kv, inp.shape[1], gout.shape[1],
+                              lambda a=a, keep=keep: call("gcd_conv_wgrad", C.byref(a), _stream()))
     _count(2 if dbias is not None else 1)
 
 
@@ -349,30 +367,31 @@ def bn_forward(x, gamma, beta, running_mean, running_var, training: bool, moment
     x = _rowmajor(x)
     n, c = x.shape
     dev = x.device
-    buf = torch.empty((4, c), dtype=torch.float32, device=dev)
-    mean, invstd, scale, shift = buf[0], buf[1], buf[2], buf[3]
     st = _stream()
+    y = torch.empty_like(x)
+    if residual is not None:
+        residual = _rowmajor(residual)
+    res_ptr, res_ld = (residual.data_ptr(), _ld(residual)) if residual is not None else (None, 0)
     if training:
+        buf = torch.empty((2, c), dtype=torch.float32, device=dev)
+        mean, invstd = buf[0], buf[1]
         if stats is None:
             stats = zeros_f64.take(2 * c, dev)
             call("gcd_bn_stats", x.data_ptr(), _ld(x), n, c, _dtype_code(x), stats.data_ptr(), st)
             _count()
-        call("gcd_bn_finalize", stats.data_ptr(), n, c, gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum),
-             running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), st)
+        call("gcd_bn_apply_train", x.data_ptr(), _ld(x), n, c, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum),
+             running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(), invstd.data_ptr(), res_ptr, res_ld, int(relu), y.data_ptr(),
+             _ld(y), _dtype_code(x), st)
         _count()
-    else:
-        call("gcd_bn_fold_eval", c, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(), float(eps),
-             scale.data_ptr(), shift.data_ptr(), st)
-        mean = running_mean
-        invstd = torch.rsqrt(running_var + eps)
-        _count()
-    y = torch.empty_like(x)
-    if residual is not None:
-        residual = _rowmajor(residual)
-    call("gcd_bn_apply", x.data_ptr(), _ld(x), n, c, scale.data_ptr(), shift.data_ptr(), residual.data_ptr() if residual is not None else None,
-         _ld(residual) if residual is not None else 0, int(relu), y.data_ptr(), _ld(y), _dtype_code(x), st)
-    _count()
-    return y, mean, invstd
+        return y, mean, invstd
+    buf = torch.empty((2, c), dtype=torch.float32, device=dev)
+    scale, shift = buf[0], buf[1]
+    call("gcd_bn_fold_eval", c, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(), float(eps),
+         scale.data_ptr(), shift.data_ptr(), st)
+    call("gcd_bn_apply", x.data_ptr(), _ld(x), n, c, scale.data_ptr(), shift.data_ptr(), res_ptr, res_ld, int(relu), y.data_ptr(), _ld(y),
+         _dtype_code(x), st)
+    _count(2)
+    return y, running_mean, torch.rsqrt(running_var + eps)
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, relu: bool, training: bool, need_dres: bool):
@@ -392,7 +411,7 @@ def bn_backward(dy, x, y, mean, invstd, gamma, relu: bool, training: bool, need_
     call("gcd_bn_backward_apply", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), yp, ldy, n, c, mean.data_ptr(), invstd.data_ptr(),
          gamma.data_ptr(), sums.data_ptr(), int(relu), int(training), dx.data_ptr(), _ld(dx), dres.data_ptr() if dres is not None else None,
          _ld(dres) if dres is not None else 0, dgamma.data_ptr(), dbeta.data_ptr(), _dtype_code(x), st)
-    _count(3)
+    _count(2)
     return dx, dres, dgamma, dbeta
 
 

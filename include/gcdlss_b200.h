@@ -216,6 +216,12 @@ int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c, int32_t dt
 int32_t gcd_bn_finalize(const double* stats, int64_t n, int32_t c, const float* gamma, const float* beta,
                         float eps, float momentum, float* running_mean, float* running_var,
                         float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* Training-mode finalise + apply in ONE launch: y = act((x - mean) * invstd * gamma + beta (+ residual)) with mean / invstd
+ * derived from stats; also writes mean / invstd [c] for the backward pass and updates the running statistics. */
+int32_t gcd_bn_apply_train(const void* x, int64_t ld_x, int64_t n, int32_t c, const double* stats, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                           float* mean, float* invstd, const void* residual, int64_t ld_res, int32_t relu, void* y,
+                           int64_t ld_y, int32_t dtype, void* stream);
 /* Eval-mode: scale/shift from running stats. */
 int32_t gcd_bn_fold_eval(int32_t c, const float* gamma, const float* beta, const float* running_mean,
                          const float* running_var, float eps, float* scale, float* shift, void* stream);

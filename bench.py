@@ -192,7 +192,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     gcdlss_b200.set_math_mode("bf16" if args.dtype == "bf16" else "fp32")
     kind, scans_per_gpu, n_points, n_classes = WORKLOADS[args.workload]
     q = synth.voxel_size(kind)
@@ -320,17 +321,17 @@ def run_ours(args):
     #     intervals include launch gaps, so they are only used for shares);  (2) kernel-only durations: the launches of one
     #     more step are captured and replayed back to back on the same tensors, all launches of a class between two events.
     roofline = None
+    # the capture step contains the gradient all-reduce, so every rank runs it; only rank 0 records and replays
+    ops.kernel_timer.captured.clear()
+    ops.kernel_timer.capture = rank == 0
+    cap_st = ME.SparseTensor(features=resident[0][1], coordinates=resident[0][0])
+    train_step(cap_st, resident[0][2])
+    ops.kernel_timer.capture = False
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         shares = {}
         for kind_k, *_rest, e0, e1 in ops.kernel_timer.records:
             shares[kind_k] = shares.get(kind_k, 0.0) + e0.elapsed_time(e1) * 1e-3
-        ops.kernel_timer.captured.clear()
-        ops.kernel_timer.capture = True
-        cap_st = ME.SparseTensor(features=resident[0][1], coordinates=resident[0][0])
-        train_step(cap_st, resident[0][2])
-        ops.kernel_timer.capture = False
-        torch.cuda.synchronize()
         mgr = cap_st.coordinate_manager
         pair_count = {}
         for km in mgr._kmaps.values():
@@ -397,6 +398,7 @@ def run_ours(args):
                 "grad_allreduce_bytes": reducer.grad_bytes() if world > 1 else 0}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

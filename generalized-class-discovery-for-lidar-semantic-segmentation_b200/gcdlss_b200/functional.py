@@ -75,25 +75,57 @@ def _use_tc(feats: torch.Tensor, c_in: int, c_out: int, kv: int) -> bool:
     return get_math_mode() == "bf16" and feats.dtype == torch.bfloat16 and ops.tc_supported(c_in, c_out, kv)
 
 
+# ---- convolution building blocks (no autograd): shared by the per-op and the fused block Functions ----------------
+def conv_fwd_impl(feats, weight, bias, kmap, out_dtype, holder):
+    w3 = _as3d(weight.detach())
+    kv, c_in, c_out = w3.shape
+    tc = _use_tc(feats, c_in, c_out, kv)
+    packed = None
+    if tc:
+        if holder is not None:
+            packed_weights.ensure(holder)
+            packed = holder._pk_fwd
+        else:
+            packed = ops.pack_weights(w3, False, False)
+    return ops.conv_forward(feats, kmap.nbr, w3, kmap.n_out, bias=bias.detach().reshape(-1) if bias is not None else None,
+                            out_dtype=out_dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed)
+
+
+def conv_dgrad_impl(gout, weight, kmap, in_dtype, holder):
+    w3 = _as3d(weight.detach())
+    kv, c_in, c_out = w3.shape
+    g = gout if gout.dtype == in_dtype else gout.to(in_dtype)
+    tc = _use_tc(g, c_out, c_in, kv)
+    packed = None
+    if tc:
+        if holder is not None and holder._pk_mirror == kmap.back_mirror:
+            packed_weights.ensure(holder)
+            packed = holder._pk_bwd
+        else:
+            packed = ops.pack_weights(w3, True, kmap.back_mirror)
+    return ops.conv_forward(g, kmap.back_nbr, w3, kmap.n_in, transpose_w=True, mirror=kmap.back_mirror, out_dtype=in_dtype,
+                            math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed)
+
+
+def conv_wgrad_impl(feats, gout, weight, kmap, want_bias_grad=False):
+    """Returns (grad_weight shaped like weight, grad_bias [1, Cout] or None)."""
+    w3 = _as3d(weight.detach())
+    kv, c_in, c_out = w3.shape
+    gw3 = ops.zeros_f32.take(w3.numel(), w3.device).view(w3.shape)
+    gb = ops.zeros_f32.take(c_out, w3.device) if want_bias_grad else None
+    tc = get_math_mode() == "bf16" and feats.dtype == torch.bfloat16 and ops.tc_supported(c_in, c_out, kv) and c_out <= 256
+    g = gout.to(torch.bfloat16) if (tc and gout.dtype != torch.bfloat16) else gout
+    ops.conv_wgrad(feats, g, kmap.pairs, kv, gw3, dbias=gb, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT)
+    return gw3.reshape(weight.shape), (gb.reshape(1, -1) if gb is not None else None)
+
+
 class SparseConvFunction(torch.autograd.Function):
     """out[o] = sum_k feats[nbr[k,o]] @ W[k] (+ bias).  ``kmap`` is a coords.KernelMap."""
 
     @staticmethod
     def forward(ctx, feats, weight, bias, kmap, out_dtype, holder=None):
-        w3 = _as3d(weight.detach())
-        kv, c_in, c_out = w3.shape
-        tc = _use_tc(feats, c_in, c_out, kv)
-        b = bias.detach().reshape(-1) if bias is not None else None
-        packed = None
-        if tc:
-            if holder is not None:
-                packed_weights.ensure(holder)
-                packed = holder._pk_fwd
-            else:
-                packed = ops.pack_weights(w3, False, False)
-        out = ops.conv_forward(feats.detach(), kmap.nbr, w3, kmap.n_out, bias=b, out_dtype=out_dtype,
-                               math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed)
-        ctx.kmap, ctx.has_bias, ctx.w_shape, ctx.holder = kmap, bias is not None, weight.shape, holder
+        out = conv_fwd_impl(feats.detach(), weight, bias, kmap, out_dtype, holder)
+        ctx.kmap, ctx.has_bias, ctx.holder = kmap, bias is not None, holder
         ctx.save_for_backward(feats, weight)
         return out
 
@@ -101,38 +133,104 @@ class SparseConvFunction(torch.autograd.Function):
     def backward(ctx, gout):
         feats, weight = ctx.saved_tensors
         kmap = ctx.kmap
-        w3 = _as3d(weight.detach())
-        kv, c_in, c_out = w3.shape
         gout = gout.contiguous()
         gfeats = gw = gb = None
         if ctx.needs_input_grad[0]:
-            g = gout if gout.dtype == feats.dtype else gout.to(feats.dtype)
-            tc = _use_tc(g, c_out, c_in, kv)
-            packed = None
-            if tc:
-                holder = ctx.holder
-                if holder is not None and holder._pk_mirror == kmap.back_mirror:
-                    packed_weights.ensure(holder)
-                    packed = holder._pk_bwd
-                else:
-                    packed = ops.pack_weights(w3, True, kmap.back_mirror)
-            gfeats = ops.conv_forward(g, kmap.back_nbr, w3, kmap.n_in, transpose_w=True, mirror=kmap.back_mirror,
-                                      out_dtype=feats.dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed)
+            gfeats = conv_dgrad_impl(gout, weight, kmap, feats.dtype, ctx.holder)
         if ctx.needs_input_grad[1]:
-            gw3 = ops.zeros_f32.take(w3.numel(), w3.device).view(w3.shape)
-            gb = ops.zeros_f32.take(c_out, w3.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-            g = gout
-            f = feats.detach()
-            tc = get_math_mode() == "bf16" and f.dtype == torch.bfloat16 and ops.tc_supported(c_in, c_out, kv) and c_out <= 256
-            if tc and g.dtype != torch.bfloat16:
-                g = g.to(torch.bfloat16)
-            ops.conv_wgrad(f, g, kmap.pairs, kv, gw3, dbias=gb, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT)
-            gw = gw3.reshape(ctx.w_shape)
-            if gb is not None:
-                gb = gb.reshape(1, -1)
+            gw, gb = conv_wgrad_impl(feats.detach(), gout, weight, kmap, ctx.has_bias and ctx.needs_input_grad[2])
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.float().sum(0, keepdim=True)
         return gfeats, gw, gb, None, None, None
+
+
+class _BnSpec:
+    """The pieces of a MinkowskiBatchNorm a fused Function needs (parameters go through apply() separately)."""
+    __slots__ = ("running_mean", "running_var", "training", "momentum", "eps")
+
+    def __init__(self, bn_module, momentum):
+        bn = bn_module.bn
+        self.running_mean, self.running_var = bn.running_mean, bn.running_var
+        self.training, self.momentum, self.eps = bn.training, momentum, bn.eps
+
+
+class ConvBnActFunction(torch.autograd.Function):
+    """conv -> batch norm -> optional ReLU as ONE autograd node (the conv->bn->relu triples of MinkUNet's trunk:
+    ref models/minkunet.py:140-147 etc.).  Same kernels as the separate modules, a third of the Python/autograd work."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, kmap, holder, bn: _BnSpec, relu: bool, out_dtype):
+        y = conv_fwd_impl(x.detach(), w, None, kmap, out_dtype, holder)
+        a, mean, invstd = ops.bn_forward(y, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var, bn.training, bn.momentum,
+                                         bn.eps, relu, None)
+        ctx.kmap, ctx.holder, ctx.relu, ctx.training = kmap, holder, relu, bn.training
+        ctx.save_for_backward(x, w, gamma, y, a if relu else None, mean, invstd)
+        return a
+
+    @staticmethod
+    def backward(ctx, ga):
+        x, w, gamma, y, a, mean, invstd = ctx.saved_tensors
+        ga = ga.contiguous()
+        if ga.dtype != y.dtype:
+            ga = ga.to(y.dtype)
+        dy, _, dgamma, dbeta = ops.bn_backward(ga, y, a, mean, invstd, gamma.detach(), ctx.relu, ctx.training, False)
+        dx = conv_dgrad_impl(dy, w, ctx.kmap, x.dtype, ctx.holder) if ctx.needs_input_grad[0] else None
+        dw, _ = conv_wgrad_impl(x.detach(), dy, w, ctx.kmap)
+        return dx, dw, dgamma, dbeta, None, None, None, None, None
+
+
+class BasicBlockFunction(torch.autograd.Function):
+    """A whole residual block (conv3-bn-relu-conv3-bn (+ 1x1 conv-bn shortcut) + add + relu) as one autograd node.
+
+    Inputs: x, then (w1, g1, b1, w2, g2, b2) and optionally (wd, gd, bd) of the shortcut; non-tensor arguments carry the
+    kernel maps, weight-image holders and batch-norm buffers."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, kmap3, kmap1, holders, bns, out_dtype):
+        h1, h2, hd = holders
+        bn1, bn2, bnd = bns
+        xd = x.detach()
+        y1 = conv_fwd_impl(xd, w1, None, kmap3, out_dtype, h1)
+        a1, m1, i1 = ops.bn_forward(y1, g1.detach(), b1.detach(), bn1.running_mean, bn1.running_var, bn1.training, bn1.momentum, bn1.eps,
+                                    True, None)
+        y2 = conv_fwd_impl(a1, w2, None, kmap3, out_dtype, h2)
+        if wd is not None:
+            yd = conv_fwd_impl(xd, wd, None, kmap1, out_dtype, hd)
+            res, md, idd = ops.bn_forward(yd, gd.detach(), bd.detach(), bnd.running_mean, bnd.running_var, bnd.training, bnd.momentum,
+                                          bnd.eps, False, None)
+        else:
+            yd = md = idd = None
+            res = xd if xd.dtype == y2.dtype else xd.to(y2.dtype)
+        out, m2, i2 = ops.bn_forward(y2, g2.detach(), b2.detach(), bn2.running_mean, bn2.running_var, bn2.training, bn2.momentum, bn2.eps,
+                                     True, res)
+        ctx.kmap3, ctx.kmap1, ctx.holders, ctx.training = kmap3, kmap1, holders, bn1.training
+        ctx.save_for_backward(x, w1, g1, w2, g2, wd, gd, y1, a1, y2, out, yd, m1, i1, m2, i2, md, idd)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w1, g1, w2, g2, wd, gd, y1, a1, y2, out, yd, m1, i1, m2, i2, md, idd = ctx.saved_tensors
+        h1, h2, hd = ctx.holders
+        tr = ctx.training
+        gout = gout.contiguous()
+        if gout.dtype != out.dtype:
+            gout = gout.to(out.dtype)
+        dy2, dres, dg2, db2 = ops.bn_backward(gout, y2, out, m2, i2, g2.detach(), True, tr, True)
+        da1 = conv_dgrad_impl(dy2, w2, ctx.kmap3, a1.dtype, h2)
+        dw2, _ = conv_wgrad_impl(a1, dy2, w2, ctx.kmap3)
+        dy1, _, dg1, db1 = ops.bn_backward(da1, y1, a1, m1, i1, g1.detach(), True, tr, False)
+        need_dx = ctx.needs_input_grad[0]
+        dx = conv_dgrad_impl(dy1, w1, ctx.kmap3, x.dtype, h1) if need_dx else None
+        dw1, _ = conv_wgrad_impl(x.detach(), dy1, w1, ctx.kmap3)
+        dwd = dgd = dbd = None
+        if wd is not None:
+            dyd, _, dgd, dbd = ops.bn_backward(dres, yd, None, md, idd, gd.detach(), False, tr, False)
+            if need_dx:
+                dx = dx + conv_dgrad_impl(dyd, wd, ctx.kmap1, x.dtype, hd)
+            dwd, _ = conv_wgrad_impl(x.detach(), dyd, wd, ctx.kmap1)
+        elif need_dx:
+            dx = dx + (dres if dres.dtype == dx.dtype else dres.to(dx.dtype))
+        return dx, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd, None, None, None, None, None
 
 
 class Im2colFunction(torch.autograd.Function):

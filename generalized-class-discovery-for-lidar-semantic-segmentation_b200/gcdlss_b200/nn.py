@@ -11,7 +11,8 @@ import torch.nn as nn
 
 from . import ops
 from .config import get_math_mode
-from .functional import BatchNormActFunction, Im2colFunction, ReLUFunction, SparseConvFunction, packed_weights
+from .functional import (BasicBlockFunction, BatchNormActFunction, ConvBnActFunction, Im2colFunction, ReLUFunction, SparseConvFunction,
+                         _BnSpec, packed_weights)
 from .sparse_tensor import CoordinateMapKey, SparseTensor
 
 
@@ -145,6 +146,17 @@ class MinkowskiBatchNorm(nn.Module):
             self.bn.num_batches_tracked.add_(self._pending_batches)
             self._pending_batches = 0
 
+    def fused_spec(self) -> _BnSpec:
+        """Bookkeeping of one forward call (batch counter, momentum) for the fused block Functions."""
+        bn = self.bn
+        momentum = bn.momentum
+        if bn.training:
+            self._pending_batches += 1
+            if momentum is None:
+                self._flush_batches()
+                momentum = 1.0 / float(bn.num_batches_tracked.item())
+        return _BnSpec(self, float(momentum or 0.0))
+
     def forward(self, input: SparseTensor, relu: bool = False, residual: SparseTensor = None) -> SparseTensor:
         bn = self.bn
         training = bn.training
@@ -191,6 +203,23 @@ class MinkowskiLinear(nn.Module):
         return input._like(self.linear(input.F))
 
 
+def conv_bn_act(conv, bn, x: SparseTensor, relu: bool = True) -> SparseTensor:
+    """``relu(bn(conv(x)))`` as one autograd node when the layer allows it (no bias, not the im2col stem),
+    otherwise the three modules in sequence.  Used by the drop-in MinkUNet trunk."""
+    thin = conv.kernel_volume > 27
+    if conv.bias is not None or thin or not isinstance(bn, MinkowskiBatchNorm):
+        return bn(conv(x), relu=relu)
+    mgr, ts_in = x.coordinate_manager, x.tensor_stride_int
+    ts_out = conv._out_stride(ts_in)
+    kmap = mgr.kernel_map(ts_in, conv.kernel_size, conv.stride, conv.TRANSPOSED)
+    feats = x._F
+    out_dtype = conv._out_dtype(feats, conv.in_channels, conv.kernel_volume)
+    if out_dtype == torch.bfloat16 and feats.dtype != torch.bfloat16:
+        feats = feats.to(torch.bfloat16)
+    out = ConvBnActFunction.apply(feats, conv.kernel, bn.bn.weight, bn.bn.bias, kmap, conv, bn.fused_spec(), relu, out_dtype)
+    return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
+
+
 def cat(*tensors) -> SparseTensor:
     """ME.cat: channel concatenation of tensors on the same coordinate map (ref minkunet.py:178,188,198,208)."""
     if len(tensors) == 1 and isinstance(tensors[0], (list, tuple)):
@@ -235,9 +264,31 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, x: SparseTensor) -> SparseTensor:
-        shortcut = x if self.downsample is None else self.downsample(x)
-        y = self.norm1(self.conv1(x), relu=True)
-        return self.norm2(self.conv2(y), relu=True, residual=shortcut)
+        ds = self.downsample
+        fusable = (self.conv1.stride == 1 and self.conv1.bias is None and self.conv2.bias is None and
+                   (ds is None or (isinstance(ds, nn.Sequential) and len(ds) == 2 and isinstance(ds[0], MinkowskiConvolution) and
+                                   isinstance(ds[1], MinkowskiBatchNorm) and ds[0].kernel_volume == 1 and ds[0].stride == 1 and
+                                   ds[0].bias is None)))
+        if not fusable:
+            shortcut = x if ds is None else ds(x)
+            y = self.norm1(self.conv1(x), relu=True)
+            return self.norm2(self.conv2(y), relu=True, residual=shortcut)
+        # one autograd node for the whole block (same kernels, far less Python / autograd work per layer)
+        mgr, ts = x.coordinate_manager, x.tensor_stride_int
+        kmap3 = mgr.kernel_map(ts, 3, 1, False)
+        kmap1 = mgr.kernel_map(ts, 1, 1, False)
+        feats = x._F
+        out_dtype = self.conv1._out_dtype(feats, self.conv1.in_channels, 27)
+        if out_dtype == torch.bfloat16 and feats.dtype != torch.bfloat16:
+            feats = feats.to(torch.bfloat16)
+        if ds is None:
+            wd = gd = bd = hd = bnd = None
+        else:
+            wd, gd, bd, hd, bnd = ds[0].kernel, ds[1].bn.weight, ds[1].bn.bias, ds[0], ds[1].fused_spec()
+        out = BasicBlockFunction.apply(feats, self.conv1.kernel, self.norm1.bn.weight, self.norm1.bn.bias, self.conv2.kernel,
+                                       self.norm2.bn.weight, self.norm2.bn.bias, wd, gd, bd, kmap3, kmap1, (self.conv1, self.conv2, hd),
+                                       (self.norm1.fused_spec(), self.norm2.fused_spec(), bnd), out_dtype)
+        return x._like(out)
 
 
 class Bottleneck(nn.Module):

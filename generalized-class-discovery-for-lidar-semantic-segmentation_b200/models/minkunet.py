@@ -12,6 +12,8 @@ import torch.nn.functional as F
 import MinkowskiEngine as ME
 from MinkowskiEngine.modules.resnet_block import BasicBlock, Bottleneck
 
+from gcdlss_b200.nn import conv_bn_act
+
 from models.resnet import ResNetBase
 
 # (conv attribute, bn attribute, block attribute) per resolution change; "p<stride>" in the names
@@ -68,15 +70,15 @@ class _UNetTrunk(ResNetBase):
 
     def _trunk(self, x):
         """Returns the outputs of block1..block8 (index 0 = block1)."""
-        cur = self.bn0(self.conv0p1s1(x), relu=True)
+        cur = conv_bn_act(self.conv0p1s1, self.bn0, x)
         skips, stages = [cur], []
         for conv, bn, block in _ENCODER:
-            cur = getattr(self, bn)(getattr(self, conv)(cur), relu=True)
+            cur = conv_bn_act(getattr(self, conv), getattr(self, bn), cur)
             cur = getattr(self, block)(cur)
             skips.append(cur)
             stages.append(cur)
         for i, (conv, bn, block) in enumerate(_DECODER):
-            cur = getattr(self, bn)(getattr(self, conv)(cur), relu=True)
+            cur = conv_bn_act(getattr(self, conv), getattr(self, bn), cur)
             cur = getattr(self, block)(ME.cat(cur, skips[3 - i]))
             stages.append(cur)
         return stages

@@ -54,6 +54,172 @@ __device__ __forceinline__ void column_reduce2(int64_t n, int c, double* __restr
   }
 }
 
+// Vectorised form (c % 4 == 0, aligned rows): a thread owns 4 consecutive channels (one 8/16-byte load per row) and a
+// row lane; a block streams kVecRows rows.  F(row, ch, a[4], b[4]).
+constexpr int kVecThreads = 256;
+constexpr int kVecRows = 256;
+template <typename F>
+__device__ __forceinline__ void column_reduce2_vec(int64_t n, int c, int rows_per_block, double* __restrict__ sums, F f) {
+  __shared__ float red[kVecThreads][9];
+  const int groups = c >> 2;                        // <= 128
+  const int lanes = kVecThreads / groups;           // row lanes per block (>= 2)
+  const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    const int64_t row_end = min((int64_t)(blockIdx.x + 1) * rows_per_block, n);
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rl; r < row_end; r += lanes) {
+      float a[4], b[4];
+      f(r, g * 4, a, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sa[j] += a[j]; sb[j] += b[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = sa[j]; red[threadIdx.x][4 + j] = sb[j]; }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] += red[l * groups + threadIdx.x][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sums[threadIdx.x * 4 + j], (double)t[j]);
+      atomicAdd(&sums[c + threadIdx.x * 4 + j], (double)t[4 + j]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_stats_vec_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, int rows_per_block, double* __restrict__ stats) {
+  column_reduce2_vec(n, c, rows_per_block, stats, [&](int64_t r, int ch, float (&a)[4], float (&b)[4]) {
+    Vec4<T>::load(x + r * ld + ch, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = a[j] * a[j];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_bwd_reduce_vec_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                                         const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                                         const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                                                         int rows_per_block, double* __restrict__ sums) {
+  column_reduce2_vec(n, c, rows_per_block, sums, [&](int64_t r, int ch, float (&a)[4], float (&b)[4]) {
+    float xv[4], yv[4] = {1.f, 1.f, 1.f, 1.f};
+    Vec4<T>::load(dy + r * ld_dy + ch, a);
+    Vec4<T>::load(x + r * ld_x + ch, xv);
+    if (relu) Vec4<T>::load(y + r * ld_y + ch, yv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (relu && !(yv[j] > 0.f)) a[j] = 0.f;
+      b[j] = a[j] * (xv[j] - mean[ch + j]) * invstd[ch + j];
+    }
+  });
+}
+
+// Streaming elementwise passes: a block first derives the per-channel constants into shared memory (fp64 batch sums ->
+// fp32 scale/shift; cheap once per block, ruinous once per thread), then streams kVecRows rows, 4 channels per thread.
+template <typename T, bool kTrain>
+__global__ void __launch_bounds__(kVecThreads) bn_apply_vec_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
+                                                                    const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, float eps, float momentum,
+                                                                    float* running_mean, float* running_var, float* __restrict__ mean_out,
+                                                                    float* __restrict__ invstd_out, const float* __restrict__ scale_in,
+                                                                    const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
+                                                                    int relu, T* __restrict__ y, int64_t ld_y) {
+  __shared__ float s_scale[512], s_shift[512];
+  for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
+    if (kTrain) {
+      const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
+      const double m = stats[ch] * inv_n;
+      double var = stats[c + ch] * inv_n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = rsqrtf((float)var + eps);
+      const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+      s_scale[ch] = g * is;
+      s_shift[ch] = b - (float)m * g * is;
+      if (blockIdx.x == 0) {
+        mean_out[ch] = (float)m;
+        invstd_out[ch] = is;
+        if (running_mean) {
+          const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+          running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+          running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+        }
+      }
+    } else {
+      s_scale[ch] = scale_in[ch];
+      s_shift[ch] = shift_in[ch];
+    }
+  }
+  __syncthreads();
+  const int groups = c >> 2;
+  const int step_r = kVecThreads / groups, step_g = kVecThreads % groups;
+  int g = threadIdx.x % groups;
+  int64_t r = (int64_t)blockIdx.x * kVecRows + threadIdx.x / groups;
+  const int64_t row_end = min((int64_t)(blockIdx.x + 1) * kVecRows, n);
+  while (r < row_end) {
+    const int ch = g * 4;
+    float v[4], rs[4] = {0.f, 0.f, 0.f, 0.f};
+    Vec4<T>::load(x + r * ld_x + ch, v);
+    if (res) Vec4<T>::load(res + r * ld_res + ch, rs);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float o = fmaf(v[j], s_scale[ch + j], s_shift[ch + j]) + rs[j];
+      v[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    Vec4<T>::store(y + r * ld_y + ch, v);
+    g += step_g; r += step_r;
+    if (g >= groups) { g -= groups; ++r; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_vec_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                                        const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                        const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
+                                                                        int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
+                                                                        int64_t ld_dres, float* dgamma, float* dbeta) {
+  __shared__ float s_k[512], s_mean[512], s_is[512], s_sg[512], s_sgx[512];
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
+    const float is = invstd[ch];
+    s_k[ch] = (gamma ? gamma[ch] : 1.f) * is;
+    s_mean[ch] = mean[ch];
+    s_is[ch] = is;
+    s_sg[ch] = training ? (float)sums[ch] * inv_n : 0.f;
+    s_sgx[ch] = training ? (float)sums[c + ch] * inv_n : 0.f;
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[ch] += (float)sums[ch];
+      if (dgamma) dgamma[ch] += (float)sums[c + ch];
+    }
+  }
+  __syncthreads();
+  const int groups = c >> 2;
+  const int step_r = kVecThreads / groups, step_g = kVecThreads % groups;
+  int g = threadIdx.x % groups;
+  int64_t r = (int64_t)blockIdx.x * kVecRows + threadIdx.x / groups;
+  const int64_t row_end = min((int64_t)(blockIdx.x + 1) * kVecRows, n);
+  while (r < row_end) {
+    const int ch = g * 4;
+    float gv[4], xv[4], yv[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
+    Vec4<T>::load(dy + r * ld_dy + ch, gv);
+    Vec4<T>::load(x + r * ld_x + ch, xv);
+    if (relu) Vec4<T>::load(y + r * ld_y + ch, yv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (relu && !(yv[j] > 0.f)) gv[j] = 0.f;
+      const float xhat = (xv[j] - s_mean[ch + j]) * s_is[ch + j];
+      o[j] = s_k[ch + j] * (gv[j] - s_sg[ch + j] - xhat * s_sgx[ch + j]);
+    }
+    Vec4<T>::store(dx + r * ld_dx + ch, o);
+    if (dres) Vec4<T>::store(dres + r * ld_dres + ch, gv);
+    g += step_g; r += step_r;
+    if (g >= groups) { g -= groups; ++r; }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRedX* kRedY) bn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, double* __restrict__ stats) {
   column_reduce2(n, c, stats, [&](int64_t r, int ch, float& a, float& b) {
@@ -297,12 +463,28 @@ template <typename T> bool vec_ok(int c, std::initializer_list<int64_t> lds, std
 
 using namespace gcd;
 
+namespace {
+inline unsigned vec_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n, kVecRows)); }
+// reductions end in one fp64 atomic per channel per block: few, fat blocks (about 4 per SM) keep the atomics rare
+inline int red_rows(int64_t n) { return (int)std::max<int64_t>(kVecRows, ceil_div(n, (int64_t)kNumSMs * 4)); }
+inline unsigned red_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n, red_rows(n))); }
+inline bool vec_shape_ok(int c) { return c % 4 == 0 && c >= 8 && c <= 512; }
+}  // namespace
+
 extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c, int32_t dtype, double* stats, void* stream) {
   GCD_REQUIRE(c >= 1 && c <= kRedX * kMaxChanIter, "gcd_bn_stats: channel count %d out of range", c);
   if (n == 0) return GCD_OK;
+  cudaStream_t st = as_stream(stream);
   dim3 block(kRedX, kRedY);
-  if (dtype == GCD_F32) bn_stats_kernel<float><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const float*)x, ld, n, c, stats);
-  else bn_stats_kernel<__nv_bfloat16><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, ld, n, c, stats);
+  if (dtype == GCD_F32) {
+    using T = float;
+    if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
+    else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
+  } else {
+    using T = __nv_bfloat16;
+    if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
+    else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
+  }
   GCD_LAUNCH_CHECK("gcd_bn_stats");
   return GCD_OK;
 }
@@ -323,22 +505,35 @@ extern "C" int32_t gcd_bn_fold_eval(int32_t c, const float* gamma, const float* 
   return GCD_OK;
 }
 
+namespace {
+template <typename T>
+void launch_apply(bool train, const void* x, int64_t ld_x, int64_t n, int c, const double* stats, const float* gamma, const float* beta,
+                  float eps, float momentum, float* rm, float* rv, float* mean, float* invstd, const float* scale, const float* shift,
+                  const void* res, int64_t ld_res, int relu, void* y, int64_t ld_y, cudaStream_t st) {
+  const bool vec = vec_ok<T>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res});
+  if (vec && vec_shape_ok(c)) {
+    if (train) bn_apply_vec_kernel<T, true><<<vec_grid(n), kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, nullptr, nullptr, (const T*)res, ld_res, relu, (T*)y, ld_y);
+    else bn_apply_vec_kernel<T, false><<<vec_grid(n), kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, (const T*)res, ld_res, relu, (T*)y, ld_y);
+    return;
+  }
+  const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(n * ((c + 3) / 4), 256));
+  if (train) {
+    if (vec) bn_apply_train_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, (const T*)res, ld_res, relu, (T*)y, ld_y);
+    else bn_apply_train_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, (const T*)res, ld_res, relu, (T*)y, ld_y);
+  } else {
+    if (vec) bn_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)res, ld_res, relu, (T*)y, ld_y);
+    else bn_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)res, ld_res, relu, (T*)y, ld_y);
+  }
+}
+}  // namespace
+
 extern "C" int32_t gcd_bn_apply(const void* x, int64_t ld_x, int64_t n, int32_t c, const float* scale, const float* shift,
                                 const void* residual, int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream) {
   if (n == 0) return GCD_OK;
+  GCD_REQUIRE(c >= 1 && c <= 512, "gcd_bn_apply: channel count %d out of range", c);
   cudaStream_t st = as_stream(stream);
-  const unsigned g = (unsigned)ceil_div(n * ((c + 3) / 4), 256);
-  if (dtype == GCD_F32) {
-    using T = float;
-    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
-      bn_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-    else bn_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-  } else {
-    using T = __nv_bfloat16;
-    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
-      bn_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-    else bn_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, scale, shift, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-  }
+  if (dtype == GCD_F32) launch_apply<float>(false, x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, residual, ld_res, relu, y, ld_y, st);
+  else launch_apply<__nv_bfloat16>(false, x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, residual, ld_res, relu, y, ld_y, st);
   GCD_LAUNCH_CHECK("gcd_bn_apply");
   return GCD_OK;
 }
@@ -347,22 +542,10 @@ extern "C" int32_t gcd_bn_apply_train(const void* x, int64_t ld_x, int64_t n, in
                                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                       float* mean, float* invstd, const void* residual, int64_t ld_res, int32_t relu, void* y,
                                       int64_t ld_y, int32_t dtype, void* stream) {
-  GCD_REQUIRE(stats && mean && invstd && c >= 1, "gcd_bn_apply_train: bad arguments");
+  GCD_REQUIRE(stats && mean && invstd && c >= 1 && c <= 512, "gcd_bn_apply_train: bad arguments");
   cudaStream_t st = as_stream(stream);
-  const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(n * ((c + 3) / 4), 256));
-  if (dtype == GCD_F32) {
-    using T = float;
-    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
-      bn_apply_train_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-    else
-      bn_apply_train_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-  } else {
-    using T = __nv_bfloat16;
-    if (vec_ok<T>(c, {ld_x, ld_y, residual ? ld_res : 0}, {x, y, residual}))
-      bn_apply_train_kernel<T, true><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-    else
-      bn_apply_train_kernel<T, false><<<g, 256, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, (const T*)residual, ld_res, relu, (T*)y, ld_y);
-  }
+  if (dtype == GCD_F32) launch_apply<float>(true, x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, nullptr, nullptr, residual, ld_res, relu, y, ld_y, st);
+  else launch_apply<__nv_bfloat16>(true, x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, nullptr, nullptr, residual, ld_res, relu, y, ld_y, st);
   GCD_LAUNCH_CHECK("gcd_bn_apply_train");
   return GCD_OK;
 }
@@ -372,37 +555,53 @@ extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const v
                                           double* sums, void* stream) {
   GCD_REQUIRE(c >= 1 && c <= kRedX * kMaxChanIter, "gcd_bn_backward_reduce: channel count %d out of range", c);
   if (n == 0) return GCD_OK;
+  cudaStream_t st = as_stream(stream);
   dim3 block(kRedX, kRedY);
-  if (dtype == GCD_F32)
-    bn_bwd_reduce_kernel<float><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const float*)dy, ld_dy, (const float*)x, ld_x, (const float*)y, ld_y, n, c, mean, invstd, relu, sums);
-  else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<reduce_grid(n), block, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, ld_dy, (const __nv_bfloat16*)x, ld_x, (const __nv_bfloat16*)y, ld_y, n, c, mean, invstd, relu, sums);
+  if (dtype == GCD_F32) {
+    using T = float;
+    if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
+      bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
+    else
+      bn_bwd_reduce_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, sums);
+  } else {
+    using T = __nv_bfloat16;
+    if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
+      bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
+    else
+      bn_bwd_reduce_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, sums);
+  }
   GCD_LAUNCH_CHECK("gcd_bn_backward_reduce");
   return GCD_OK;
 }
+
+namespace {
+template <typename T>
+void launch_bwd_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y, int64_t n, int c,
+                      const float* mean, const float* invstd, const float* gamma, const double* sums, int relu, int training, void* dx,
+                      int64_t ld_dx, void* dres, int64_t ld_dres, float* dgamma, float* dbeta, cudaStream_t st) {
+  const bool vec = vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres});
+  if (vec && vec_shape_ok(c)) {
+    bn_bwd_apply_vec_kernel<T><<<vec_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
+    return;
+  }
+  const unsigned g = (unsigned)ceil_div(n * ((c + 3) / 4), 256);
+  if (vec) bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
+  else bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
+}
+}  // namespace
 
 extern "C" int32_t gcd_bn_backward_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y,
                                          int64_t n, int32_t c, const float* mean, const float* invstd, const float* gamma,
                                          const double* sums, int32_t relu, int32_t training, void* dx, int64_t ld_dx, void* dres,
                                          int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream) {
+  GCD_REQUIRE(c >= 1 && c <= 512, "gcd_bn_backward_apply: channel count %d out of range", c);
   cudaStream_t st = as_stream(stream);
   if (n > 0) {
-    const unsigned g = (unsigned)ceil_div(n * ((c + 3) / 4), 256);
-    if (dtype == GCD_F32) {
-      using T = float;
-      if (vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}))
-        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
-      else
-        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
-    } else {
-      using T = __nv_bfloat16;
-      if (vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}))
-        bn_bwd_apply_kernel<T, true><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
-      else
-        bn_bwd_apply_kernel<T, false><<<g, 256, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);
-    }
+    if (dtype == GCD_F32) launch_bwd_apply<float>(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, dx, ld_dx, dres, ld_dres, dgamma, dbeta, st);
+    else launch_bwd_apply<__nv_bfloat16>(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, dx, ld_dx, dres, ld_dres, dgamma, dbeta, st);
+  } else if (dgamma || dbeta) {
+    bn_param_grad_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(sums, c, dgamma, dbeta);
   }
-  if (n <= 0 && (dgamma || dbeta)) bn_param_grad_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(sums, c, dgamma, dbeta);
   GCD_LAUNCH_CHECK("gcd_bn_backward_apply");
   return GCD_OK;
 }

@@ -32,6 +32,7 @@ WORKLOADS = {
     "kitti_b4": ("kitti", 4, None, 17),          # BASELINE.json configs[1]
     "nuscenes_b16": ("nuscenes", 16, None, 14),  # configs[2]
 }
+# configs[3] (Stage-2 mean-teacher step) is exercised by tests/test_gpu_stage2.py and tools/bench_stage2.py
 METRIC = "MinkUNet fwd+bwd scans/sec"
 
 

@@ -1,0 +1,123 @@
+"""Step harnesses: the tensor flow of the reference's two Lightning ``training_step``s around the hot path, without
+Lightning (not installable here).  They exist so the path can be exercised and timed the way its callers use it:
+
+* ``stage1_step``  — ``ExpPretrain.training_step`` (ref modules/exp.py:249-267): SparseTensor -> model -> CE.
+* ``Stage2Harness.step`` — ``ExpMergeDiscover_LaserMix_MeanTeacher_NCCAdaptive.training_step``
+  (ref modules/exp_merge_mean_teacher.py:2772-2875): teacher and student share one SparseTensor (and therefore all
+  kernel maps), CE on labelled voxels + 200 * MSE(student, teacher) on unlabelled ones, teacher pseudo-labels gathered
+  back to points, LaserMix by pitch-angle bands (ref :1731-1787), inline ``sparse_quantize`` of the mixed points
+  (batch column divided by the voxel size too, as in the reference), second student forward, backward, SGD, EMA.
+  The loss terms that are dense torch on logits (calibration, hinge, k-means/Hungarian) are outside the hot path and
+  are not reproduced.  Everything stays on the GPU (the reference round-trips LaserMix through numpy).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .functional import devoxelize
+from .quantize import sparse_quantize_gpu
+from .sparse_tensor import SparseTensor
+
+
+def stage1_step(model, feats, bcoords, labels):
+    st = SparseTensor(features=feats.float(), coordinates=bcoords.int())
+    out = model(st)
+    return F.cross_entropy(out["logits"], labels.long())
+
+
+def laser_mix(points_sup, points_unsup, feats_sup, feats_unsup, labels_sup, labels_unsup, num_areas: int,
+              pitch_angles=(-25.0, 3.0)):
+    """Pitch-angle band swap between one labelled and one unlabelled scan (ref exp_merge_mean_teacher.py:1731-1787).
+    Points are [P, 3] sensor-frame xyz.  Returns two mixed scans (points, feats, labels)."""
+    lo, hi = pitch_angles[0] / 180 * math.pi, pitch_angles[1] / 180 * math.pi
+
+    def band(p):
+        pitch = torch.atan2(p[:, 2], torch.sqrt(p[:, 0] ** 2 + p[:, 1] ** 2)).clamp(lo + 1e-5, hi - 1e-5)
+        # angle_list = linspace(hi, lo, num_areas + 1); band i covers (angle[i+1], angle[i]]
+        return torch.clamp(((hi - pitch) / (hi - lo) * num_areas).floor().long(), 0, num_areas - 1)
+
+    bs, bu = band(points_sup), band(points_unsup)
+    even_s, even_u = (bs % 2 == 0), (bu % 2 == 0)
+    mix1 = (torch.cat([points_sup[even_s], points_unsup[~even_u]]), torch.cat([feats_sup[even_s], feats_unsup[~even_u]]),
+            torch.cat([labels_sup[even_s], labels_unsup[~even_u]]))
+    mix2 = (torch.cat([points_unsup[even_u], points_sup[~even_s]]), torch.cat([feats_unsup[even_u], feats_sup[~even_s]]),
+            torch.cat([labels_unsup[even_u], labels_sup[~even_s]]))
+    return mix1, mix2
+
+
+class Stage2Harness:
+    def __init__(self, student, teacher, optimizer, voxel_size: float, mse_coeff: float = 200.0, ema_momentum: float = 0.01,
+                 num_areas=(3, 4, 5, 6), reducer=None):
+        self.student, self.teacher, self.opt = student, teacher, optimizer
+        self.voxel_size, self.mse_coeff, self.ema_momentum, self.num_areas = voxel_size, mse_coeff, ema_momentum, num_areas
+        self.reducer = reducer
+        self._step = 0
+        for p in self.teacher.parameters():
+            p.requires_grad_(False)                                        # ref :155, :251-254
+
+    def step(self, sup, unsup):
+        """sup / unsup: dicts with voxel-level 'coords' [M,4] int32, 'feats' [M,C], point-level 'points' (list of [P,3]),
+        'point_feats' (list of [P,C]); sup also 'labels' [M] (voxels) and 'point_labels' (list of [P]); unsup also
+        'inverse_maps' (list of [P] int64, voxel of each point *within its scan*)."""
+        n_sup_scans = len(sup["points"])
+        unsup_coords = unsup["coords"].clone()
+        unsup_coords[:, 0] += n_sup_scans                                  # ref :2797
+        coords_cat = torch.cat((sup["coords"], unsup_coords), 0)
+        feats_cat = torch.cat((sup["feats"], unsup["feats"]), 0)
+        st = SparseTensor(features=feats_cat.float(), coordinates=coords_cat.int())
+        with torch.no_grad():
+            out_t = self.teacher(st)                                       # shares st's kernel maps with the student
+        out_s = self.student(st)
+        n_sup = sup["coords"].shape[0]
+        loss = F.cross_entropy(out_s["logits"][:n_sup], sup["labels"].long())
+        prob_s = F.softmax(out_s["logits"][n_sup:], dim=1)
+        prob_t = F.softmax(out_t["logits"][n_sup:], dim=1)
+        loss = loss + F.mse_loss(prob_s, prob_t.detach()) * self.mse_coeff
+        max_prob_t, target_t = torch.max(prob_t, dim=1)
+        # voxel -> point devoxelisation of the pseudo labels.  The reference concatenates the scans' inverse maps without
+        # offsetting the second by the first scan's voxel count (ref :2787-2790); preserved, not fixed.
+        inv_cat = torch.cat(unsup["inverse_maps"])
+        pts_prob = devoxelize(max_prob_t[:, None], inv_cat)[:, 0]
+        pts_label = devoxelize(target_t[:, None].float(), inv_cat)[:, 0].long()
+        pts_label[pts_prob < 0.9] = -1
+        # LaserMix: scan i of the labelled half with scan i of the unlabelled half
+        areas = self.num_areas[self._step % len(self.num_areas)]
+        mixed_pts, mixed_feats, mixed_labels = [], [], []
+        off = 0
+        for i in range(min(n_sup_scans, len(unsup["points"]))):
+            pu = unsup["points"][i]
+            lu = pts_label[off:off + pu.shape[0]]
+            off += pu.shape[0]
+            for b, (mp, mf, ml) in enumerate(laser_mix(sup["points"][i], pu, sup["point_feats"][i], unsup["point_feats"][i],
+                                                       sup["point_labels"][i], lu, areas)):
+                bcol = torch.full((mp.shape[0], 1), float(2 * i + b), device=mp.device)
+                mixed_pts.append(torch.cat([bcol, mp], 1))
+                mixed_feats.append(mf)
+                mixed_labels.append(ml)
+        lm_points = torch.cat(mixed_pts)
+        # inline quantisation of the mixed batch: the batch column is divided by the voxel size too (ref :2856-2861)
+        lm_coords, lm_umap, _ = sparse_quantize_gpu(lm_points, self.voxel_size)
+        mix_st = SparseTensor(features=torch.cat(mixed_feats)[lm_umap].float(), coordinates=lm_coords)
+        out_mix = self.student(mix_st)
+        mix_labels = torch.cat(mixed_labels)[lm_umap]
+        if bool((mix_labels >= 0).any()):
+            loss = loss + 0.1 * F.cross_entropy(out_mix["logits"], mix_labels.long(), ignore_index=-1)
+        else:
+            loss = loss + 0.0 * out_mix["logits"].sum()
+        if self.reducer is not None:
+            self.reducer.reset()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        with torch.no_grad():                                              # EMA teacher <- student, parameters only (ref :246-248)
+            ps, pt = list(self.student.parameters()), list(self.teacher.parameters())
+            torch._foreach_mul_(pt, 1.0 - self.ema_momentum)
+            torch._foreach_add_(pt, ps, alpha=self.ema_momentum)
+        self._step += 1
+        return loss.detach()

@@ -4,8 +4,8 @@ are not installable here.  Same class names, constructor arguments and returned 
 
 Voxel types: 'minkunet' runs on the sm_100a quantise + hash-dedup kernels; 'dynamic' and
 'cylindrical' are per-point coordinate formulas (torch elementwise, as in the reference's own
-cylindrical branch); 'hard' (fixed points-per-voxel buffers, mmcv ``hard_voxelize``) is listed as
-"next" in SURVEY 8(f) rank 4 and raises.
+cylindrical branch); 'hard' (fixed points-per-voxel buffers, mmcv ``hard_voxelize``) dedups and groups with the
+hash / counting-sort kernels.
 """
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -44,7 +44,7 @@ class VoxelLayer(nn.Module):
         """Dynamic voxelisation (max_num_points == -1): per-point (z, y, x) grid coordinates, -1 outside
         the range (mmcv ``dynamic_voxelize`` semantics, ref models/voxelizer.py:453-461)."""
         if self.max_num_points != -1 and self.max_voxels[0] != -1:
-            raise NotImplementedError("hard voxelisation (fixed max_num_points buffers) is not implemented yet (SURVEY 8(f) rank 4)")
+            return self.hard_voxelize(input, self.max_voxels[0] if self.training else self.max_voxels[1])
         lo = input.new_tensor(self.point_cloud_range[:3])
         vs = input.new_tensor(self.voxel_size)
         grid = torch.tensor(self.grid_shape, device=input.device)
@@ -53,6 +53,34 @@ class VoxelLayer(nn.Module):
         c = c[:, [2, 1, 0]]
         c[bad] = -1
         return c
+
+
+def _hard_voxelize(self, points: Tensor, max_voxels: int):
+    """mmcv ``hard_voxelize`` (deterministic flavour, ref models/voxelizer.py:463-485): voxels in first-occurrence
+    order of their points, the first ``max_num_points`` points of each voxel in point order, at most ``max_voxels``
+    voxels.  Returns (voxels [M, max_points, C] zero padded, coors [M, 3] as (z, y, x), num_points [M]).
+    Dedup and grouping run on the hash / counting-sort kernels; the rest is index arithmetic."""
+    from gcdlss_b200 import ops
+    lo = points.new_tensor(self.point_cloud_range[:3])
+    vs = points.new_tensor(self.voxel_size)
+    grid = torch.tensor(self.grid_shape, device=points.device)
+    c = torch.floor((points[:, :3] - lo) / vs).int()
+    keep = torch.nonzero(((c >= 0) & (c < grid)).all(1)).reshape(-1)
+    c, pts = c.index_select(0, keep).contiguous(), points.index_select(0, keep)
+    uniq, inv, _ = ops.unique_rows(c, order=0)
+    m = min(int(uniq.shape[0]), int(max_voxels))
+    seg_off, order = ops.csr_build(inv, uniq.shape[0])
+    vox_of_sorted = inv.index_select(0, order.long())
+    rank = torch.arange(order.shape[0], device=points.device) - seg_off.long().index_select(0, vox_of_sorted)
+    sel = (rank < self.max_num_points) & (vox_of_sorted < m)
+    voxels = points.new_zeros((m, self.max_num_points, points.shape[1]))
+    voxels[vox_of_sorted[sel], rank[sel]] = pts.index_select(0, order.long()[sel])
+    num_points = torch.clamp(seg_off[1:m + 1] - seg_off[:m], max=self.max_num_points).int()
+    coors = c.index_select(0, uniq[:m])[:, [2, 1, 0]].contiguous()
+    return voxels, coors, num_points
+
+
+VoxelLayer.hard_voxelize = _hard_voxelize
 
 
 class Voxelizer(nn.Module):
@@ -109,7 +137,20 @@ class Voxelizer(nn.Module):
         if self.voxel_type == 'minkunet':
             return _q.voxelize_minkunet(points, self.voxel_layer.voxel_size, self.batch_first, self.max_voxels, self.training)
         voxel_dict = dict()
-        if self.voxel_type == 'dynamic':
+        if self.voxel_type == 'hard':
+            voxels, coors, num_points, voxel_centers = [], [], [], []
+            for i, res in enumerate(points):
+                res_voxels, res_coors, res_num_points = self.voxel_layer(res)
+                res_voxel_centers = (res_coors[:, [2, 1, 0]] + 0.5) * res_voxels.new_tensor(self.voxel_layer.voxel_size) + \
+                    res_voxels.new_tensor(self.voxel_layer.point_cloud_range[0:3])
+                voxels.append(res_voxels)
+                coors.append(F.pad(res_coors, (1, 0), mode='constant', value=i))
+                num_points.append(res_num_points)
+                voxel_centers.append(res_voxel_centers)
+            voxel_dict['num_points'] = torch.cat(num_points, dim=0)
+            voxel_dict['voxel_centers'] = torch.cat(voxel_centers, dim=0)
+            voxels, coors = torch.cat(voxels, dim=0), torch.cat(coors, dim=0)
+        elif self.voxel_type == 'dynamic':
             coors = [F.pad(self.voxel_layer(res), (1, 0), mode='constant', value=i) for i, res in enumerate(points)]
             voxels = torch.cat(points, dim=0)
             coors = torch.cat(coors, dim=0)
@@ -124,8 +165,6 @@ class Voxelizer(nn.Module):
                 voxels.append(torch.cat((polar, res[:, :2], res[:, 3:]), dim=-1))
             voxels = torch.cat(voxels, dim=0)
             coors = torch.cat(coors, dim=0)
-        elif self.voxel_type == 'hard':
-            raise NotImplementedError("voxel_type='hard' is not implemented yet (SURVEY 8(f) rank 4)")
         else:
             raise ValueError(f'Invalid voxelization type {self.voxel_type}')
         voxel_dict['voxels'] = voxels

@@ -58,6 +58,9 @@ struct FwdParams {
   const float* bias;
   void* out; int64_t ld_out; int out_is_bf16;
   int stages;
+#ifdef GCD_TC_PROFILE
+  long long* dbg;
+#endif
 };
 
 struct SmemLayout {
@@ -150,9 +153,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 
     uint32_t st = 0, ph = 0;                   // stage being filled, parity of its empty barrier
     uint32_t tile_seq = 0;
+#ifdef GCD_TC_PROFILE
+    long long prof_wait = 0, prof_iters = 0, prof_table = 0; const long long prof_t0 = clock64();
+#endif
     int table[kTableRegs];
     if ((int64_t)blockIdx.x < n_work) load_table(blockIdx.x, table);
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+#ifdef GCD_TC_PROFILE
+      const long long ct0 = clock64();
+#endif
       named_bar_sync(1, kProducerThreads + 32);  // previous tile's table no longer needed by anyone (weight warp included)
       uint32_t my_mask = 0;
 #pragma unroll
@@ -171,6 +180,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       for (int w = 0; w < kProducerWarps; ++w) mask |= s_any[w];
       if (t == 0) s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
       rotate(mask, mask, lo_mask);
+#ifdef GCD_TC_PROFILE
+      prof_table += clock64() - ct0;
+#endif
 
       while (mask) {
         const int k = __ffs(mask) - 1;
@@ -186,7 +198,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #pragma unroll
         for (int q = 0; q < (kNQ ? kNQ : 8); ++q) {
           if (!kNQ && q >= nq) break;
+#ifdef GCD_TC_PROFILE
+          const long long cw0 = clock64();
+#endif
           mbar_wait_addr(empty0 + st * 8, ph ^ 1);
+#ifdef GCD_TC_PROFILE
+          prof_wait += clock64() - cw0; ++prof_iters;
+#endif
           if (q + 1 < nq || last_active) {
             const uint32_t a_stage = a_base + st * kABytes;
             cp_async_16(a_stage, s0 + q * (kChunkK * 2), n0);
@@ -200,6 +218,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       }
     }
     cp_async_wait_all();                                 // nothing may still be writing smem at exit
+#ifdef GCD_TC_PROFILE
+    if (p.dbg && t == 32) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; }
+#endif
   } else if (warp == kWeightWarp) {
     // ===================================================================== weight producer (TMA bulk copies)
     // Walks the same (tile, offset, slice) sequence as the gather warps and, per stage, posts the transaction
@@ -224,11 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
         const uint8_t* w_k = w_tile + (int64_t)k * nq * p.c_out * kRowBytes;
         for (int q = 0; q < nq; ++q) {
           mbar_wait(&empty_bar[st], ph ^ 1);
-          if (leader) {
-            mbar_arrive_expect_tx(&full_bar[st], b_bytes);
-            bulk_g2s(b_base + st * b_bytes, w_k + (int64_t)q * p.c_out * kRowBytes, b_bytes, &full_bar[st]);
-          }
-          __syncwarp();
+          mbar_arrive_expect_tx_pred(&full_bar[st], b_bytes, leader ? 1u : 0u);
+          bulk_g2s_pred(b_base + st * b_bytes, w_k + (int64_t)q * p.c_out * kRowBytes, b_bytes, &full_bar[st], leader ? 1u : 0u);
           if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
         }
       }
@@ -245,30 +263,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     const bool leader = elect_one();
     uint32_t st = 0, ph = 0, tile_seq = 0;
     uint64_t da = da0, db = db0;
+#ifdef GCD_TC_PROFILE
+    long long prof_full = 0, prof_acc = 0; const long long prof_t0 = clock64();
+#endif
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
       const uint32_t buf = tile_seq & 1;
+#ifdef GCD_TC_PROFILE
+      const long long ca0 = clock64();
+#endif
       mbar_wait(&tmem_empty[buf], ((tile_seq >> 1) & 1) ^ 1);
+#ifdef GCD_TC_PROFILE
+      prof_acc += clock64() - ca0;
+#endif
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * kAccStride;
       int n_iters = 1, q = 0;
       uint32_t accumulate = 0;
       for (int it = 0; it < n_iters; ++it) {
+#ifdef GCD_TC_PROFILE
+        const long long cf0 = clock64();
+#endif
         mbar_wait(&full_bar[st], ph);
+#ifdef GCD_TC_PROFILE
+        prof_full += clock64() - cf0;
+#endif
         tc_fence_after();
         if (it == 0) n_iters = s_iters[tile_seq & (kTileRing - 1)];
         const int ksteps = (q == nq - 1) ? last_ksteps : kChunkK / 16;
-        if (leader) {
-          for (int ks = 0; ks < ksteps; ++ks) mma_bf16_ss(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)ks);
-          mma_commit(&empty_bar[st]);
-        }
+        // predicated issue slots (no branch: divergence + reconvergence around an elected lane costs ~230 cycles per stage)
+#pragma unroll
+        for (int ks = 0; ks < kChunkK / 16; ++ks)
+          mma_bf16_ss_pred(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)ks, (leader && ks < ksteps) ? 1u : 0u);
+        mma_commit_pred(&empty_bar[st], leader ? 1u : 0u);
         accumulate = 1;
-        __syncwarp();
         if (++q == nq) q = 0;
         if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0; db = db0; } else { da += da_step; db += db_step; }
       }
-      if (leader) mma_commit(&tmem_full[buf]);
-      __syncwarp();
+      mma_commit_pred(&tmem_full[buf], leader ? 1u : 0u);
     }
+#ifdef GCD_TC_PROFILE
+    if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[4] = clock64() - prof_t0; d[5] = prof_full; d[6] = prof_acc; }
+#endif
   } else {
     // ===================================================================== epilogue
     const int ew = warp - kEpilogueWarp0;      // == warp % 4: the TMEM lane quarter this warp may read
@@ -508,17 +543,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
         for (int it = 0; it < n_stages; ++it) {
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < kWgPairs / 16; ++ks) mma_bf16_ss(tmem_d, da + ks * k_step, db + ks * k_step, idesc, accumulate | (uint32_t)ks);
-            mma_commit(&empty_bar[st]);
-          }
+          for (int ks = 0; ks < kWgPairs / 16; ++ks)
+            mma_bf16_ss_pred(tmem_d, da + ks * k_step, db + ks * k_step, idesc, accumulate | (uint32_t)ks, leader ? 1u : 0u);
+          mma_commit_pred(&empty_bar[st], leader ? 1u : 0u);
           accumulate = 1;
-          __syncwarp();
           if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0; db = db0; } else { da += stage_step; db += stage_step; }
         }
-        if (leader) mma_commit(&tmem_full[buf]);
-        __syncwarp();
+        mma_commit_pred(&tmem_full[buf], leader ? 1u : 0u);
       }
     }
   } else if (warp < kMmaWarp) {
@@ -596,6 +628,10 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   return GCD_OK;
 }
 
+#ifdef GCD_TC_PROFILE
+static long long* g_debug_buffer = nullptr;
+#endif
+
 bool conv_forward_tc_supported(const gcd_conv_args* a) {
   return a->in_dtype == GCD_BF16 && a->c_in % 16 == 0 && a->c_out % 16 == 0 && a->c_in >= 16 && a->c_out >= 16 &&
          a->c_out <= 512 && a->kv <= kMaxKV && a->w_packed != nullptr && a->ld_in % 8 == 0 &&
@@ -618,6 +654,9 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   if (const char* e = getenv("GCD_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));   // tuning aid
   if (stages < 2) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
+#ifdef GCD_TC_PROFILE
+  p.dbg = g_debug_buffer;
+#endif
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;
   using Kernel = void (*)(const FwdParams);
@@ -674,6 +713,11 @@ extern "C" int32_t gcd_conv_pack_weights_batched(const void* descs, int32_t n_de
   GCD_LAUNCH_CHECK("gcd_conv_pack_weights_batched");
   return GCD_OK;
 }
+
+#ifdef GCD_TC_PROFILE
+// tuning builds only (make PROFILE=1): per-CTA cycle counters of the forward kernel's producer / MMA warps
+extern "C" int32_t gcd_debug_set_buffer(void* device_buffer) { gcd::g_debug_buffer = static_cast<long long*>(device_buffer); return 0; }
+#endif
 
 extern "C" int32_t gcd_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t kv) {
   return c_in % 16 == 0 && c_out % 16 == 0 && c_in >= 16 && c_out >= 16 && c_out <= 512 && kv <= 27;

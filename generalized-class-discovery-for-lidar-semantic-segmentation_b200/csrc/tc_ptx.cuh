@@ -94,6 +94,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// predicated forms for the elected lane of a converged warp (no branch, see mma_bf16_ss_pred)
+__device__ __forceinline__ void mbar_arrive_expect_tx_pred(uint64_t* bar, uint32_t bytes, uint32_t pred) {
+  asm volatile("{\n\t.reg .b64 st;\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+               ::"r"(smem_u32(bar)), "r"(bytes), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_pred(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+               "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "r"(pred) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
@@ -114,6 +125,27 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Predicated forms: every lane of the (converged) warp executes the instruction slot, only lanes with pred != 0 issue.
+// Measured on B200: wrapping the issue in `if (elected) { ... } __syncwarp();` costs ~230 cycles per loop iteration
+// for the divergence / reconvergence alone; the predicated form has no branch.
+__device__ __forceinline__ void mma_bf16_ss_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pred(uint64_t* bar, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(pred)
       : "memory");
 }
 // All previously issued MMAs of this thread complete -> one arrival on the mbarrier.

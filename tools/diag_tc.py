@@ -35,5 +35,16 @@ for (cin, cout, ts) in ((96, 96, 1), (128, 96, 1), (32, 32, 2), (64, 64, 4), (12
     us_f = timeit(lambda: ops.conv_forward(x, km.nbr, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=packed))
     dw = torch.zeros_like(w)
     us_w = timeit(lambda: ops.conv_wgrad(x, g, km.pairs, 27, dw, math_mode=1))
+    import ctypes as C
+    from gcdlss_b200 import _cabi
+    if hasattr(_cabi.lib(), "gcd_debug_set_buffer"):
+        dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+        _cabi.lib().gcd_debug_set_buffer(C.c_void_p(dbg.data_ptr()))
+        ops.conv_forward(x, km.nbr, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=packed)
+        torch.cuda.synchronize()
+        _cabi.lib().gcd_debug_set_buffer(None)
+        d = dbg.view(148, 8).double(); d = d[d[:, 0] > 0].max(0).values
+        print(f"   [profile build] producer: total={d[0]:.0f} table={d[1]:.0f} wait_empty={d[2]:.0f} iters={d[3]:.0f} busy/iter={(d[0]-d[1]-d[2])/max(d[3],1):.0f}"
+              f" | mma: total={d[4]:.0f} wait_full={d[5]:.0f} wait_acc={d[6]:.0f} busy/iter={(d[4]-d[5]-d[6])/max(d[3],1):.0f}")
     print(f"{cin}->{cout} ts{ts}: n={n} pairs={pairs} density={pairs/(27*n):.2f} | fwd {us_f:.1f} us {flops/us_f/1e6:.1f} TFLOP/s alg "
           f"({27*n*cin*cout*2/us_f/1e6:.0f} dense-equiv) | wgrad {us_w:.1f} us {flops/us_w/1e6:.1f} TFLOP/s")

@@ -203,7 +203,7 @@ def run_ours(args):
     torch.manual_seed(1234)
     model = MinkUNetBase(num_classes=n_classes).to(dev).train()
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, fused=True)     # ref modules/exp.py:155-174
-    reducer = GradBucketReducer(model.parameters())
+    reducer = GradBucketReducer(model.parameters()) if world > 1 else None
 
     n_batches = 3
     host_batches = make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches)
@@ -217,11 +217,15 @@ def run_ours(args):
     prefetcher = BatchPrefetcher(dev)
 
     def train_step(st, labels):
+        if reducer is None:
+            opt.zero_grad(set_to_none=True)        # gradients are taken over from the wgrad kernels' buffers, no accumulate pass
+        else:
+            reducer.reset()                        # .grad are views of the flat all-reduce buckets: zero them in place
         out = model(st)
         loss = torch.nn.functional.cross_entropy(out["logits"], labels)
-        reducer.reset()
         loss.backward()
-        reducer.finish()
+        if reducer is not None:
+            reducer.finish()
         opt.step()
         return loss
 
@@ -300,15 +304,12 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     launches0 = ops.launch_counter["calls"]
-    ops.kernel_timer.enabled = True
-    ops.kernel_timer.records.clear()
     total_ms = timed(step_resident, args.steps)
-    ops.kernel_timer.enabled = False
     launches = ops.launch_counter["calls"] - launches0
     if args.no_e2e:
         e2e_ms = float("nan")
     else:
-        for i in range(min(args.warmup, 3)):
+        for i in range(max(args.warmup, 2 * n_batches + 2)):     # same rule as above: the e2e path allocates its own shapes
             step_e2e(i)
         e2e_ms = timed(step_e2e, args.steps)
     clock_info = clocks.stop() if rank == 0 else None
@@ -318,9 +319,10 @@ def run_ours(args):
     e2e_value = scans_total / (e2e_ms / 1e3)
 
     # ---- live roofline of the dominant kernel class ----------------------------------------------------------------
-    # (1) share of the step: CUDA events around every conv launch inside the timed region (host-bound steps make these
-    #     intervals include launch gaps, so they are only used for shares);  (2) kernel-only durations: the launches of one
-    #     more step are captured and replayed back to back on the same tensors, all launches of a class between two events.
+    # The timed region issues whole blocks through gcd_block_forward/backward (no per-launch hooks on the host).  For the
+    # kernel-only durations one more step runs through the per-launch path (same kernels, same order), its convolution
+    # launches are captured and then replayed back to back on the same tensors, all launches of a class between two CUDA
+    # events; the share of the step is that kernel time over the measured step time.
     roofline = None
     # the capture step contains the gradient all-reduce, so every rank runs it; only rank 0 records and replays
     ops.kernel_timer.captured.clear()
@@ -330,9 +332,6 @@ def run_ours(args):
     ops.kernel_timer.capture = False
     torch.cuda.synchronize()
     if rank == 0:
-        shares = {}
-        for kind_k, *_rest, e0, e1 in ops.kernel_timer.records:
-            shares[kind_k] = shares.get(kind_k, 0.0) + e0.elapsed_time(e1) * 1e-3
         mgr = cap_st.coordinate_manager
         pair_count = {}
         for km in mgr._kmaps.values():
@@ -375,7 +374,7 @@ def run_ours(args):
                         "peak_source": (peaks["source"] + " bf16_tflops (burst: kernels timed alone, back to back)") if tensor else "nominal fp32 FMA peak",
                         "algorithmic_gflop_per_step": info["flops"] / 1e9, "launches_per_step": info["launches"],
                         "avg_launch_us": info["time"] / info["launches"] * 1e6, "kernel_ms_per_step": info["time"] * 1e3,
-                        "share_of_step_by_events": {k: v / (total_ms / 1e3) for k, v in shares.items()},
+                        "share_of_step": {k: v["time"] * 1e3 / (total_ms / args.steps) for k, v in classes.items()},
                         "by_kernel": {k: {"kernel_ms_per_step": v["time"] * 1e3, "tflops": v["flops"] / v["time"] / 1e12,
                                           "launches_per_step": v["launches"]} for k, v in classes.items()}}
 
@@ -396,7 +395,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + 8 * scans_per_gpu,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
-                "grad_allreduce_bytes": reducer.grad_bytes() if world > 1 else 0}
+                "grad_allreduce_bytes": reducer.grad_bytes() if reducer is not None else 0}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

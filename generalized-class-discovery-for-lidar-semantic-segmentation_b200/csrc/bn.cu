@@ -220,6 +220,244 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_vec_kernel(const T* 
   }
 }
 
+// ---- 16-byte-wide streaming kernels (c % V == 0 with V = 4 fp32 / 8 bf16 channels per thread) -----------------------
+// Sized by the host so that small tensors still fill the machine: an elementwise block takes `rows_per_block` rows with
+// about two to eight 16-byte items per thread (two in flight at a time); deep MinkUNet levels have few rows and many
+// channels, and blocks of 256 rows left most SMs idle there (16..70 blocks, 75 us for a 4 MB tensor).
+template <typename T> struct VecW;
+template <> struct VecW<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecW<__nv_bfloat16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// Walks the (row, channel group) items of a block two at a time: item i of thread t is t + i * kVecThreads.
+struct ItemWalk {
+  int g; int64_t r; int step_g; int step_r; int groups;
+  __device__ __forceinline__ ItemWalk(int groups_, int64_t row0) : groups(groups_) {
+    g = threadIdx.x % groups; r = row0 + threadIdx.x / groups;
+    step_g = kVecThreads % groups; step_r = kVecThreads / groups;
+  }
+  __device__ __forceinline__ void next() { g += step_g; r += step_r; if (g >= groups) { g -= groups; ++r; } }
+};
+
+template <typename T, int V, typename F>
+__device__ __forceinline__ void column_reduce2_wide(int64_t n, int c, int rows_per_block, double* __restrict__ sums, F f) {
+  __shared__ float red[kVecThreads][2 * V + 1];
+  const int groups = c / V;                         // <= 128
+  const int lanes = kVecThreads / groups;           // row lanes per block (>= 2)
+  const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float sa[V], sb[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+  if (rl < lanes) {
+    const int64_t row_end = min((int64_t)(blockIdx.x + 1) * rows_per_block, n);
+    int64_t r = (int64_t)blockIdx.x * rows_per_block + rl;
+    for (; r + lanes < row_end; r += 2 * lanes) {   // two rows in flight
+      float a0[V], b0[V], a1[V], b1[V];
+      f(r, g * V, a0, b0);
+      f(r + lanes, g * V, a1, b1);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { sa[j] += a0[j] + a1[j]; sb[j] += b0[j] + b1[j]; }
+    }
+    if (r < row_end) {
+      float a0[V], b0[V];
+      f(r, g * V, a0, b0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { sa[j] += a0[j]; sb[j] += b0[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) { red[threadIdx.x][j] = sa[j]; red[threadIdx.x][V + j] = sb[j]; }
+  __syncthreads();
+  // one thread per (channel, quantity): 2c <= 1024 sums over the row lanes
+  for (int q = threadIdx.x; q < 2 * c; q += kVecThreads) {
+    const int ch = q < c ? q : q - c;
+    const int grp = ch / V, j = (ch % V) + (q < c ? 0 : V);
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[l * groups + grp][j];
+    atomicAdd(&sums[q], (double)t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_stats_wide_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, int rows_per_block, double* __restrict__ stats) {
+  constexpr int V = VecW<T>::V;
+  column_reduce2_wide<T, V>(n, c, rows_per_block, stats, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
+    VecW<T>::load(x + r * ld + ch, a);
+#pragma unroll
+    for (int j = 0; j < V; ++j) b[j] = a[j] * a[j];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_bwd_reduce_wide_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                                          const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                                          const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                                                          int rows_per_block, double* __restrict__ sums) {
+  constexpr int V = VecW<T>::V;
+  __shared__ float s_mean[512], s_is[512];
+  for (int ch = threadIdx.x; ch < c; ch += kVecThreads) { s_mean[ch] = mean[ch]; s_is[ch] = invstd[ch]; }
+  __syncthreads();
+  column_reduce2_wide<T, V>(n, c, rows_per_block, sums, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
+    float xv[V], yv[V];
+    VecW<T>::load(dy + r * ld_dy + ch, a);
+    VecW<T>::load(x + r * ld_x + ch, xv);
+    if (relu) VecW<T>::load(y + r * ld_y + ch, yv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (relu && !(yv[j] > 0.f)) a[j] = 0.f;
+      b[j] = a[j] * (xv[j] - s_mean[ch + j]) * s_is[ch + j];
+    }
+  });
+}
+
+template <typename T, bool kTrain>
+__global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
+                                                                     const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps, float momentum,
+                                                                     float* running_mean, float* running_var, float* __restrict__ mean_out,
+                                                                     float* __restrict__ invstd_out, const float* __restrict__ scale_in,
+                                                                     const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
+                                                                     int relu, T* __restrict__ y, int64_t ld_y, int rows_per_block) {
+  constexpr int V = VecW<T>::V;
+  __shared__ float s_scale[512], s_shift[512];
+  for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
+    if (kTrain) {
+      const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
+      const double m = stats[ch] * inv_n;
+      double var = stats[c + ch] * inv_n - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = rsqrtf((float)var + eps);
+      const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+      s_scale[ch] = g * is;
+      s_shift[ch] = b - (float)m * g * is;
+      if (blockIdx.x == 0) {
+        mean_out[ch] = (float)m;
+        invstd_out[ch] = is;
+        if (running_mean) {
+          const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+          running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+          running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+        }
+      }
+    } else {
+      s_scale[ch] = scale_in[ch];
+      s_shift[ch] = shift_in[ch];
+    }
+  }
+  __syncthreads();
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(row0 + rows_per_block, n);
+  ItemWalk a(c / V, row0);
+  while (a.r < row_end) {
+    ItemWalk b = a; b.next();
+    const bool two = b.r < row_end;
+    float va[V], vb[V], ra[V], rb[V];
+    VecW<T>::load(x + a.r * ld_x + a.g * V, va);
+    if (two) VecW<T>::load(x + b.r * ld_x + b.g * V, vb);
+    if (res) {
+      VecW<T>::load(res + a.r * ld_res + a.g * V, ra);
+      if (two) VecW<T>::load(res + b.r * ld_res + b.g * V, rb);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float o = fmaf(va[j], s_scale[a.g * V + j], s_shift[a.g * V + j]);
+      if (res) o += ra[j];
+      va[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    VecW<T>::store(y + a.r * ld_y + a.g * V, va);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float o = fmaf(vb[j], s_scale[b.g * V + j], s_shift[b.g * V + j]);
+        if (res) o += rb[j];
+        vb[j] = relu ? fmaxf(o, 0.f) : o;
+      }
+      VecW<T>::store(y + b.r * ld_y + b.g * V, vb);
+    }
+    a = b; a.next();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_wide_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                                         const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                         const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
+                                                                         int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
+                                                                         int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
+  constexpr int V = VecW<T>::V;
+  __shared__ float s_k[512], s_mean[512], s_is[512], s_sg[512], s_sgx[512];
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
+    const float is = invstd[ch];
+    s_k[ch] = (gamma ? gamma[ch] : 1.f) * is;
+    s_mean[ch] = mean[ch];
+    s_is[ch] = is;
+    s_sg[ch] = training ? (float)sums[ch] * inv_n : 0.f;
+    s_sgx[ch] = training ? (float)sums[c + ch] * inv_n : 0.f;
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[ch] += (float)sums[ch];
+      if (dgamma) dgamma[ch] += (float)sums[c + ch];
+    }
+  }
+  __syncthreads();
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = min(row0 + rows_per_block, n);
+  ItemWalk a(c / V, row0);
+  while (a.r < row_end) {
+    ItemWalk b = a; b.next();
+    const bool two = b.r < row_end;
+    float ga[V], gb[V], xa[V], xb[V], ya[V], yb[V], o[V];
+    VecW<T>::load(dy + a.r * ld_dy + a.g * V, ga);
+    VecW<T>::load(x + a.r * ld_x + a.g * V, xa);
+    if (relu) VecW<T>::load(y + a.r * ld_y + a.g * V, ya);
+    if (two) {
+      VecW<T>::load(dy + b.r * ld_dy + b.g * V, gb);
+      VecW<T>::load(x + b.r * ld_x + b.g * V, xb);
+      if (relu) VecW<T>::load(y + b.r * ld_y + b.g * V, yb);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int ch = a.g * V + j;
+      if (relu && !(ya[j] > 0.f)) ga[j] = 0.f;
+      const float xhat = (xa[j] - s_mean[ch]) * s_is[ch];
+      o[j] = s_k[ch] * (ga[j] - s_sg[ch] - xhat * s_sgx[ch]);
+    }
+    VecW<T>::store(dx + a.r * ld_dx + a.g * V, o);
+    if (dres) VecW<T>::store(dres + a.r * ld_dres + a.g * V, ga);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int ch = b.g * V + j;
+        if (relu && !(yb[j] > 0.f)) gb[j] = 0.f;
+        const float xhat = (xb[j] - s_mean[ch]) * s_is[ch];
+        o[j] = s_k[ch] * (gb[j] - s_sg[ch] - xhat * s_sgx[ch]);
+      }
+      VecW<T>::store(dx + b.r * ld_dx + b.g * V, o);
+      if (dres) VecW<T>::store(dres + b.r * ld_dres + b.g * V, gb);
+    }
+    a = b; a.next();
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRedX* kRedY) bn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, double* __restrict__ stats) {
   column_reduce2(n, c, stats, [&](int64_t r, int ch, float& a, float& b) {
@@ -469,6 +707,27 @@ inline unsigned vec_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil
 inline int red_rows(int64_t n) { return (int)std::max<int64_t>(kVecRows, ceil_div(n, (int64_t)kNumSMs * 4)); }
 inline unsigned red_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n, red_rows(n))); }
 inline bool vec_shape_ok(int c) { return c % 4 == 0 && c >= 8 && c <= 512; }
+// 16-byte path: V channels per thread, every leading dimension a multiple of V, every pointer 16-byte aligned
+template <typename T> bool wide_ok(int c, std::initializer_list<int64_t> lds, std::initializer_list<const void*> ptrs) {
+  const int V = 16 / (int)sizeof(T);
+  if (c % V || c < 2 * V || c > 512) return false;
+  for (int64_t ld : lds) if (ld % V) return false;
+  for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) % 16)) return false;
+  return true;
+}
+// elementwise passes: ~8 blocks per SM when the tensor allows, never less than two items per thread
+template <typename T> int wide_rows(int64_t n, int c) {
+  const int groups = c / (16 / (int)sizeof(T));
+  const int64_t min_rows = ceil_div(2 * kVecThreads, groups);
+  return (int)std::min<int64_t>(std::max<int64_t>(ceil_div(n, (int64_t)kNumSMs * 8), min_rows), 4096);
+}
+// reductions: ~4 blocks per SM (one fp64 atomic per channel per block), at least four rows per row lane
+template <typename T> int wide_red_rows(int64_t n, int c) {
+  const int groups = c / (16 / (int)sizeof(T));
+  const int64_t min_rows = (int64_t)(kVecThreads / groups) * 4;
+  return (int)std::max<int64_t>(ceil_div(n, (int64_t)kNumSMs * 4), min_rows);
+}
+inline unsigned rows_grid(int64_t n, int rows) { return (unsigned)std::max<int64_t>(1, ceil_div(n, rows)); }
 }  // namespace
 
 extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c, int32_t dtype, double* stats, void* stream) {
@@ -478,11 +737,13 @@ extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c,
   dim3 block(kRedX, kRedY);
   if (dtype == GCD_F32) {
     using T = float;
-    if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
+    if (wide_ok<T>(c, {ld}, {x})) { const int rows = wide_red_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
+    else if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
     else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
   } else {
     using T = __nv_bfloat16;
-    if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
+    if (wide_ok<T>(c, {ld}, {x})) { const int rows = wide_red_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
+    else if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
     else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
   }
   GCD_LAUNCH_CHECK("gcd_bn_stats");
@@ -510,6 +771,13 @@ template <typename T>
 void launch_apply(bool train, const void* x, int64_t ld_x, int64_t n, int c, const double* stats, const float* gamma, const float* beta,
                   float eps, float momentum, float* rm, float* rv, float* mean, float* invstd, const float* scale, const float* shift,
                   const void* res, int64_t ld_res, int relu, void* y, int64_t ld_y, cudaStream_t st) {
+  if (wide_ok<T>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res})) {
+    const int rows = wide_rows<T>(n, c);
+    const unsigned g = rows_grid(n, rows);
+    if (train) bn_apply_wide_kernel<T, true><<<g, kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, nullptr, nullptr, (const T*)res, ld_res, relu, (T*)y, ld_y, rows);
+    else bn_apply_wide_kernel<T, false><<<g, kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, (const T*)res, ld_res, relu, (T*)y, ld_y, rows);
+    return;
+  }
   const bool vec = vec_ok<T>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res});
   if (vec && vec_shape_ok(c)) {
     if (train) bn_apply_vec_kernel<T, true><<<vec_grid(n), kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, nullptr, nullptr, (const T*)res, ld_res, relu, (T*)y, ld_y);
@@ -559,13 +827,19 @@ extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const v
   dim3 block(kRedX, kRedY);
   if (dtype == GCD_F32) {
     using T = float;
-    if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
+    if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr})) {
+      const int rows = wide_red_rows<T>(n, c);
+      bn_bwd_reduce_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
+    } else if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
       bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
     else
       bn_bwd_reduce_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, sums);
   } else {
     using T = __nv_bfloat16;
-    if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
+    if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr})) {
+      const int rows = wide_red_rows<T>(n, c);
+      bn_bwd_reduce_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
+    } else if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
       bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
     else
       bn_bwd_reduce_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, sums);
@@ -579,6 +853,11 @@ template <typename T>
 void launch_bwd_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y, int64_t n, int c,
                       const float* mean, const float* invstd, const float* gamma, const double* sums, int relu, int training, void* dx,
                       int64_t ld_dx, void* dres, int64_t ld_dres, float* dgamma, float* dbeta, cudaStream_t st) {
+  if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres})) {
+    const int rows = wide_rows<T>(n, c);
+    bn_bwd_apply_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta, rows);
+    return;
+  }
   const bool vec = vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres});
   if (vec && vec_shape_ok(c)) {
     bn_bwd_apply_vec_kernel<T><<<vec_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta);

@@ -72,6 +72,34 @@ class WgradArgs(C.Structure):
     ]
 
 
+class ConvBnUnit(C.Structure):
+    """gcd_convbn: one conv -> batch-norm unit of a fused block."""
+    _fields_ = [
+        ("nbr", C.c_void_p), ("n_in", C.c_int64), ("n_out", C.c_int64),
+        ("back_nbr", C.c_void_p), ("back_mirror", C.c_int32),
+        ("pair_in", C.c_void_p), ("pair_out", C.c_void_p), ("pair_off", C.c_void_p), ("n_pairs", C.c_int64),
+        ("kv", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32),
+        ("w", C.c_void_p), ("w_packed_fwd", C.c_void_p), ("w_packed_bwd", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+        ("eps", C.c_float), ("momentum", C.c_float),
+        ("stats", C.c_void_p), ("sums", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+        ("dw", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+    ]
+
+
+class BlockArgs(C.Structure):
+    """gcd_block_args."""
+    _fields_ = [
+        ("u1", ConvBnUnit), ("u2", ConvBnUnit), ("ud", ConvBnUnit),
+        ("has_u2", C.c_int32), ("has_ud", C.c_int32), ("relu1", C.c_int32), ("dtype", C.c_int32),
+        ("x", C.c_void_p), ("ld_x", C.c_int64),
+        ("y1", C.c_void_p), ("a1", C.c_void_p), ("y2", C.c_void_p), ("yd", C.c_void_p), ("rd", C.c_void_p), ("out", C.c_void_p),
+        ("gout", C.c_void_p), ("dy2", C.c_void_p), ("dres", C.c_void_p), ("da1", C.c_void_p), ("dy1", C.c_void_p),
+        ("dyd", C.c_void_p), ("dx", C.c_void_p), ("dxd", C.c_void_p),
+        ("need_dx", C.c_int32), ("launches", C.c_int32),
+    ]
+
+
 _i32, _i64, _vp, _sz, _f32, _f64 = C.c_int32, C.c_int64, C.c_void_p, C.c_size_t, C.c_float, C.c_double
 
 # name -> (restype, argtypes).  Every symbol declared in include/gcdlss_b200.h is listed here;
@@ -115,6 +143,8 @@ PROTOTYPES = {
     "gcd_rows_gather": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "gcd_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "gcd_csr_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "gcd_block_forward": (_i32, [C.POINTER(BlockArgs), _vp]),
+    "gcd_block_backward": (_i32, [C.POINTER(BlockArgs), _vp]),
     "gcd_segment_reduce": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
 }
 

@@ -9,8 +9,10 @@ import weakref
 
 import torch
 
+import ctypes as C
+
 from . import ops
-from ._cabi import MATH_BF16_TC, MATH_FP32_SIMT
+from ._cabi import MATH_BF16_TC, MATH_FP32_SIMT, BlockArgs, call
 from .config import get_math_mode
 
 class PackedWeights:
@@ -231,6 +233,143 @@ class BasicBlockFunction(torch.autograd.Function):
         elif need_dx:
             dx = dx + (dres if dres.dtype == dx.dtype else dres.to(dx.dtype))
         return dx, dw1, dg1, db1, dw2, dg2, db2, dwd, dgd, dbd, None, None, None, None, None
+
+
+# ---- whole blocks sequenced in C (gcd_block_forward / gcd_block_backward) ----------------------------------------
+def fused_block_ok(x: torch.Tensor, out_dtype, training: bool) -> bool:
+    """The C-sequenced block path: training mode, one activation dtype, no per-launch instrumentation."""
+    return (training and _FUSED_C and x.dtype == out_dtype and not ops.kernel_timer.enabled and not ops.kernel_timer.capture)
+
+
+_FUSED_C = __import__("os").environ.get("GCDLSS_FUSED_BLOCKS", "1") != "0"
+
+
+def _fill_unit(u, w, gamma, beta, bn, kmap, holder, tc, with_grad):
+    w3 = _as3d(w)
+    kv, c_in, c_out = w3.shape
+    nbr = kmap.nbr
+    u.nbr = nbr.data_ptr() if nbr is not None else None
+    u.n_in, u.n_out = kmap.n_in, kmap.n_out
+    u.kv, u.c_in, u.c_out = kv, c_in, c_out
+    u.w = w.data_ptr()
+    if tc:
+        if holder._pk_mirror != kmap.back_mirror:
+            raise RuntimeError("packed dgrad image orientation does not match the kernel map")
+        packed_weights.ensure(holder)
+        u.w_packed_fwd = holder._pk_fwd.data_ptr()
+    u.gamma, u.beta = gamma.data_ptr(), beta.data_ptr()
+    u.running_mean, u.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+    u.eps, u.momentum = bn.eps, bn.momentum
+    if with_grad:
+        back = kmap.back_nbr
+        u.back_nbr = back.data_ptr() if back is not None else None
+        u.back_mirror = int(kmap.back_mirror)
+        if tc:
+            u.w_packed_bwd = holder._pk_bwd.data_ptr()
+        pairs = kmap.pairs
+        if pairs is not None:
+            u.pair_in, u.pair_out, u.pair_off = pairs[0].data_ptr(), pairs[1].data_ptr(), pairs[2].data_ptr()
+            u.n_pairs = pairs[0].shape[0]
+    return kv * c_in * c_out
+
+
+class FusedBlockFunction(torch.autograd.Function):
+    """conv-bn(-relu) or a whole residual block, forward and backward each ONE call into the C library
+    (gcd_block_forward / gcd_block_backward sequence the same kernels the per-op Functions launch).
+
+    ``w2 is None``: single unit, output relu?(bn(conv(x))).  Otherwise the BasicBlock with identity (``wd is None``)
+    or 1x1-conv + bn shortcut."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, kmap, kmap1, holders, bns, relu1):
+        xd = ops._rowmajor(x.detach())
+        dev, dt = xd.device, xd.dtype
+        has_u2, has_ud = w2 is not None, wd is not None
+        c_in, c = w1.shape[-2], w1.shape[-1]
+        n_out = kmap.n_out
+        with_grad = any(ctx.needs_input_grad)      # grad mode itself is off inside Function.forward
+        units = 1 + int(has_u2) + int(has_ud)
+        slab = torch.empty((2 * units, n_out, c), dtype=dt, device=dev)
+        moments = torch.empty((2 * units, c), dtype=torch.float32, device=dev)
+        stats = ops.zeros_f64.take(2 * units * c, dev)
+        a = BlockArgs()
+        a.has_u2, a.has_ud, a.relu1 = int(has_u2), int(has_ud), int(relu1)
+        a.dtype = ops._dtype_code(xd)
+        a.x, a.ld_x = xd.data_ptr(), ops._ld(xd)
+        esz = slab.element_size() * n_out * c
+        base, mbase, sbase = slab.data_ptr(), moments.data_ptr(), stats.data_ptr()
+        h1, h2, hd = holders
+        bn1, bn2, bnd = bns
+        tc = dt == torch.bfloat16 and get_math_mode() == "bf16"
+        sizes = [_fill_unit(a.u1, w1, g1, b1, bn1, kmap, h1, tc and h1._pk_tc, with_grad)]
+        a.u1.stats, a.u1.mean, a.u1.invstd = sbase, mbase, mbase + 4 * c
+        a.y1, a.a1 = base, base + esz
+        out = slab[1]
+        if has_u2:
+            sizes.append(_fill_unit(a.u2, w2, g2, b2, bn2, kmap, h2, tc and h2._pk_tc, with_grad))
+            a.u2.stats, a.u2.mean, a.u2.invstd = sbase + 16 * c, mbase + 8 * c, mbase + 12 * c
+            a.y2, a.out = base + 2 * esz, base + 3 * esz
+            out = slab[3]
+            if has_ud:
+                sizes.append(_fill_unit(a.ud, wd, gd, bd, bnd, kmap1, hd, tc and hd._pk_tc, with_grad))
+                a.ud.stats, a.ud.mean, a.ud.invstd = sbase + 32 * c, mbase + 16 * c, mbase + 20 * c
+                a.yd, a.rd = base + 4 * esz, base + 5 * esz
+        call("gcd_block_forward", C.byref(a), ops._stream())
+        ops._count(a.launches)
+        ctx.args, ctx.sizes, ctx.c, ctx.c_in = a, sizes, c, c_in
+        ctx.w_shapes = (w1.shape, w2.shape if has_u2 else None, wd.shape if has_ud else None)
+        ctx.keep = (xd, slab, moments, kmap, kmap1, holders)      # everything the struct points into
+        ctx.x_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, c, c_in = ctx.args, ctx.c, ctx.c_in
+        xd, slab = ctx.keep[0], ctx.keep[1]
+        dev, dt = slab.device, slab.dtype
+        gout = ops._rowmajor(gout)
+        if gout.dtype != dt:
+            gout = gout.to(dt)
+        if gout.stride(0) != c and gout.shape[0] > 1:
+            gout = gout.contiguous()
+        has_u2, has_ud = bool(a.has_u2), bool(a.has_ud)
+        n_out, n_in = a.u1.n_out, a.u1.n_in
+        units = 1 + int(has_u2) + int(has_ud)
+        need_dx = ctx.needs_input_grad[0]
+        gslab = torch.empty((3 if has_u2 else 1, n_out, c), dtype=dt, device=dev)
+        esz = gslab.element_size() * n_out * c
+        gb = gslab.data_ptr()
+        dx = torch.empty((n_in, c_in), dtype=dt, device=dev) if need_dx else None
+        dxd = torch.empty((n_in, c_in), dtype=dt, device=dev) if (need_dx and has_ud) else None
+        sums = ops.zeros_f64.take(2 * units * c, dev)
+        sizes = ctx.sizes
+        grads = ops.zeros_f32.take(sum(sizes) + 2 * units * c, dev)
+        gp, sp = grads.data_ptr(), sums.data_ptr()
+        a.gout = gout.data_ptr()
+        a.need_dx = int(need_dx)
+        a.dx = dx.data_ptr() if dx is not None else None
+        a.dxd = dxd.data_ptr() if dxd is not None else None
+        outs, off = [], 0
+        for i, (u, size) in enumerate(zip((a.u1, a.u2, a.ud), sizes)):
+            u.sums = sp + 16 * c * i
+            u.dw, u.dgamma, u.dbeta = gp + 4 * off, gp + 4 * (off + size), gp + 4 * (off + size + c)
+            outs.append((grads[off:off + size].view(ctx.w_shapes[i]), grads[off + size:off + size + c], grads[off + size + c:off + size + 2 * c]))
+            off += size + 2 * c
+        if has_u2:
+            a.dy2, a.dres, a.da1 = gb, gb + esz, gb + 2 * esz
+            a.dy1 = a.da1             # the first unit's BN backward runs in place on the dgrad of the second
+            a.dyd = a.dres            # likewise the shortcut's on the residual gradient
+        else:
+            a.dy1 = gb
+        call("gcd_block_backward", C.byref(a), ops._stream())
+        ops._count(a.launches)
+        if dx is not None and dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+        none3 = (None, None, None)
+        g1 = outs[0]
+        g2 = outs[1] if has_u2 else none3
+        g3 = outs[2] if has_ud else none3
+        return (dx,) + g1 + g2 + g3 + (None, None, None, None, None)
 
 
 class Im2colFunction(torch.autograd.Function):

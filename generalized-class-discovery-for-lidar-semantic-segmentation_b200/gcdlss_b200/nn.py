@@ -11,8 +11,8 @@ import torch.nn as nn
 
 from . import ops
 from .config import get_math_mode
-from .functional import (BasicBlockFunction, BatchNormActFunction, ConvBnActFunction, Im2colFunction, ReLUFunction, SparseConvFunction,
-                         _BnSpec, packed_weights)
+from .functional import (BasicBlockFunction, BatchNormActFunction, ConvBnActFunction, FusedBlockFunction, Im2colFunction, ReLUFunction,
+                         SparseConvFunction, _BnSpec, fused_block_ok, packed_weights)
 from .sparse_tensor import CoordinateMapKey, SparseTensor
 
 
@@ -216,7 +216,11 @@ def conv_bn_act(conv, bn, x: SparseTensor, relu: bool = True) -> SparseTensor:
     out_dtype = conv._out_dtype(feats, conv.in_channels, conv.kernel_volume)
     if out_dtype == torch.bfloat16 and feats.dtype != torch.bfloat16:
         feats = feats.to(torch.bfloat16)
-    out = ConvBnActFunction.apply(feats, conv.kernel, bn.bn.weight, bn.bn.bias, kmap, conv, bn.fused_spec(), relu, out_dtype)
+    if fused_block_ok(feats, out_dtype, bn.bn.training):
+        out = FusedBlockFunction.apply(feats, conv.kernel, bn.bn.weight, bn.bn.bias, None, None, None, None, None, None, kmap, None,
+                                       (conv, None, None), (bn.fused_spec(), None, None), relu)
+    else:
+        out = ConvBnActFunction.apply(feats, conv.kernel, bn.bn.weight, bn.bn.bias, kmap, conv, bn.fused_spec(), relu, out_dtype)
     return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
 
 
@@ -285,6 +289,11 @@ class BasicBlock(nn.Module):
             wd = gd = bd = hd = bnd = None
         else:
             wd, gd, bd, hd, bnd = ds[0].kernel, ds[1].bn.weight, ds[1].bn.bias, ds[0], ds[1].fused_spec()
+        if fused_block_ok(feats, out_dtype, self.norm1.bn.training and self.norm2.bn.training and (ds is None or ds[1].bn.training)):
+            out = FusedBlockFunction.apply(feats, self.conv1.kernel, self.norm1.bn.weight, self.norm1.bn.bias, self.conv2.kernel,
+                                           self.norm2.bn.weight, self.norm2.bn.bias, wd, gd, bd, kmap3, kmap1, (self.conv1, self.conv2, hd),
+                                           (self.norm1.fused_spec(), self.norm2.fused_spec(), bnd), True)
+            return x._like(out)
         out = BasicBlockFunction.apply(feats, self.conv1.kernel, self.norm1.bn.weight, self.norm1.bn.bias, self.conv2.kernel,
                                        self.norm2.bn.weight, self.norm2.bn.bias, wd, gd, bd, kmap3, kmap1, (self.conv1, self.conv2, hd),
                                        (self.norm1.fused_spec(), self.norm2.fused_spec(), bnd), out_dtype)

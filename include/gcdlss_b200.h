@@ -258,6 +258,50 @@ int32_t gcd_csr_build(const int64_t* idx, int64_t n_points, int64_t n_segments, 
 int32_t gcd_segment_reduce(const float* in, int64_t ld_in, const int32_t* seg_off, const int32_t* order,
                            int64_t n_segments, int32_t c, int32_t mode, float* out, int64_t ld_out, void* stream);
 
+/* ------------------------------------------------------------------ fused blocks -------- */
+/* conv -> batch norm (-> ReLU) triples and whole residual blocks sequenced from C: one call per block and
+ * direction instead of one per launch (the step is launch-bound from Python).  Replaces, as one unit,
+ * MinkowskiEngine's BasicBlock.forward / its autograd backward (MinkowskiEngine/modules/resnet_block.py,
+ * imported at ref models/minkunet.py:30) and the conv-bn-relu triples of ref models/minkunet.py:140-147.
+ * Training mode only (batch statistics); all pointers device, caller allocated.  Activations of a block are
+ * dense row-major [n, c] of one dtype. */
+typedef struct {
+  const int32_t* nbr;        /* forward table [kv][n_out], NULL = identity (kv == 1) */
+  int64_t n_in, n_out;
+  const int32_t* back_nbr;   /* table of the transposed map [kv][n_in] (dgrad) */
+  int32_t back_mirror;       /* 1: dgrad uses W[kv-1-k]^T (self-transposed stride-1 maps) */
+  const int32_t* pair_in; const int32_t* pair_out; const int32_t* pair_off;   /* wgrad pair lists (NULL = identity) */
+  int64_t n_pairs;
+  int32_t kv, c_in, c_out;
+  const float* w;            /* fp32 [kv, c_in, c_out] */
+  const void* w_packed_fwd;  /* tcgen05 operand images; NULL selects the fp32 SIMT kernels */
+  const void* w_packed_bwd;
+  const float* gamma; const float* beta; float* running_mean; float* running_var;
+  float eps, momentum;
+  double* stats;             /* [2 c_out] zero on entry of gcd_block_forward  */
+  double* sums;              /* [2 c_out] zero on entry of gcd_block_backward */
+  float* mean; float* invstd;                /* [c_out] each: written by forward, read by backward */
+  float* dw; float* dgamma; float* dbeta;    /* zero on entry of backward, accumulated into */
+} gcd_convbn;
+
+typedef struct {
+  gcd_convbn u1, u2, ud;     /* first unit; second unit (has_u2); shortcut 1x1 conv + bn (has_ud) */
+  int32_t has_u2, has_ud;
+  int32_t relu1;             /* single unit (has_u2 == 0): apply ReLU after the batch norm */
+  int32_t dtype;             /* gcd_dtype of every activation / gradient buffer */
+  const void* x; int64_t ld_x;
+  /* forward buffers: y = conv result, a1 = relu(bn(y1)), rd = bn(yd), out = relu(bn(y2) + shortcut) */
+  void* y1; void* a1; void* y2; void* yd; void* rd; void* out;
+  /* backward buffers */
+  const void* gout;          /* gradient of out (of a1 for a single unit) */
+  void* dy2; void* dres; void* da1; void* dy1; void* dyd; void* dx; void* dxd;
+  int32_t need_dx;
+  int32_t launches;          /* out: kernels launched by the call */
+} gcd_block_args;
+
+int32_t gcd_block_forward(gcd_block_args* args, void* stream);
+int32_t gcd_block_backward(gcd_block_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,8 +30,12 @@ class OpChecker:
         self.records = []
 
     def __enter__(self):
-        from gcdlss_b200 import ops
+        from gcdlss_b200 import functional, ops
         self.ops = ops
+        # per-launch path: the C-sequenced blocks issue the same kernels in the same order without passing through these
+        # Python hooks (tests/test_gpu_fused_block.py holds the two paths bit-identical)
+        self._fn, self._fused = functional, functional._FUSED_C
+        functional._FUSED_C = False
         self._saved = (ops.bn_backward, ops.conv_forward, ops.conv_wgrad)
         real_bn_bwd, real_conv_fwd, real_wgrad = self._saved
         rec = self.records
@@ -92,6 +96,7 @@ class OpChecker:
 
     def __exit__(self, *exc):
         self.ops.bn_backward, self.ops.conv_forward, self.ops.conv_wgrad = self._saved
+        self._fn._FUSED_C = self._fused
         return False
 
     def worst(self):

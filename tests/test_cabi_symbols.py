@@ -62,6 +62,26 @@ def test_struct_layout_matches_c():
     assert (w.pair_in.offset, w.n_pairs.offset, w.kv.offset, w.dw.offset, w.n_out.offset, w.math_mode.offset) == (32, 56, 64, 80, 96, 112)
 
 
+def test_block_struct_layout_against_gcc(tmp_path):
+    """sizeof / offsetof of the fused-block structs as gcc lays them out == the ctypes mirror."""
+    fields_u = [f[0] for f in _cabi.ConvBnUnit._fields_]
+    fields_b = [f[0] for f in _cabi.BlockArgs._fields_]
+    prog = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{HEADER}"', "int main(void){",
+            'printf("%zu %zu\\n", sizeof(gcd_convbn), sizeof(gcd_block_args));']
+    prog += [f'printf("%zu\\n", offsetof(gcd_convbn, {f}));' for f in fields_u]
+    prog += [f'printf("%zu\\n", offsetof(gcd_block_args, {f}));' for f in fields_b]
+    prog += ["return 0;}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    sizes, offs = [int(v) for v in out[:2]], [int(v) for v in out[2:]]
+    assert sizes == [ctypes.sizeof(_cabi.ConvBnUnit), ctypes.sizeof(_cabi.BlockArgs)]
+    assert offs[:len(fields_u)] == [getattr(_cabi.ConvBnUnit, f).offset for f in fields_u]
+    assert offs[len(fields_u):] == [getattr(_cabi.BlockArgs, f).offset for f in fields_b]
+
+
 def test_product_code_never_imports_the_oracle():
     pkg = _paths.PKG_DIR
     for dirpath, _, files in os.walk(pkg):

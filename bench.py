@@ -301,7 +301,7 @@ def run_ours(args):
                   f"alloc_retries {ms1['num_alloc_retries']}", file=sys.stderr)
         gc.callbacks.remove(_gc_cb)
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("GCDLSS_BENCH_NO_CLOCKS"):       # (diagnosis only: the sampler is part of the contract)
         clocks.start()
     launches0 = ops.launch_counter["calls"]
     total_ms = timed(step_resident, args.steps)

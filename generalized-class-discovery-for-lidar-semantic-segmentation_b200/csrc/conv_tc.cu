@@ -38,7 +38,6 @@ constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
 constexpr int kEpilogueWarp0 = kProducerWarps;        // 8: (8 + i) % 4 == i, the TMEM lane quarter rule
 constexpr int kMmaWarp = kProducerWarps + 4;          // 12
-constexpr int kWeightWarp = kProducerWarps + 5;       // 13: issues the weight bulk copies of the forward kernel
 constexpr int kTcThreads = kProducerThreads + kEpilogueThreads + 64;
 constexpr int kMaxKV = 27;
 constexpr int kMaxStages = 8;
@@ -60,6 +59,7 @@ struct FwdParams {
   int stages;
 #ifdef GCD_TC_PROFILE
   long long* dbg;
+  int ablate;                      // profile build only: 1 = no MMA issue, 2 = no gather copies, 4 = weight copies of 16 B
 #endif
 };
 
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
   const uint32_t rot = (blockIdx.x * 11u) % (uint32_t)p.kv;   // per-CTA rotation of the offset order (spreads weight reads)
 
   if (threadIdx.x == 0) {
-    // full: one completion-triggered arrival per gather thread + the weight warp's arrive.expect_tx
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads + 1); mbar_init(&empty_bar[s], 1); }
+    // full: one completion-triggered arrival per lane of the owning producer warp + its lane 0's arrive.expect_tx (weights)
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], (S <= 4 ? 64 : 32) + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     fence_mbar_init();
   }
@@ -126,18 +126,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
   };
 
   if (warp < kProducerWarps) {
-    // ===================================================================== gather producers
+    // ===================================================================== gather producers (stage owners)
+    // Producer warp (or warp pair) w OWNS the stages of iterations g == w (mod PA), PA = min(8 / G, stages): it waits for the slot, posts
+    // the weight slice (one bulk copy on the TMA engine) and gathers all 128 rows x 64 channels itself (32 cp.async per
+    // lane), then hands the stage over with completion-triggered arrivals.  Up to PA stages are being filled at once
+    // and the per-stage fixed costs (barrier wait, index loads, arrive, loop control) are paid by one warp instead of
+    // by all eight in lock-step -- measured (tools/ubench/ldgsts_gather.cu): 270 -> ~130 cycles per stage.
     const int t = threadIdx.x;                 // 0..255
     const int trow = t & (kTileM - 1);         // tile row this thread loads table entries for
     const int tpar = t >> 7;                   // ... for offsets k = tpar, tpar + 2, ...
     const int chunk = lane & 7;
-    const int row0 = warp * 4 + (lane >> 3);   // this thread's rows are row0 + 32 j, j = 0..3
-    const uint32_t doff0 = row0 * kRowBytes + ((chunk ^ (row0 & 7)) << 4);   // + 4096 j for the other rows
+    const int rsub = lane >> 3;                // this lane's rows are rsub + 4 j, j = 0..31
+    const uint32_t d_even = rsub * kRowBytes + ((chunk ^ rsub) << 4);                 // j even: row & 7 == rsub
+    const uint32_t d_odd = (rsub + 4) * kRowBytes + ((chunk ^ (rsub + 4)) << 4);      // j odd:  row & 7 == rsub + 4
     const char* col_base = reinterpret_cast<const char*>(p.in + chunk * 8);
     const int64_t ld_bytes = p.ld_in * 2;
     const bool last_active = chunk * 8 < last_width;
-    const uint32_t a_base = smem_u32(smem + L.a_off) + doff0;
+    const uint32_t a_base = smem_u32(smem + L.a_off);
+    const uint32_t b_base = smem_u32(smem + L.b_off);
+    const uint32_t b_bytes = L.b_bytes;
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    // Few, fat stages (wide N tiles: S <= 4): two warps share a stage (16 rows per lane each) so that all eight warps
+    // stay busy and a stage is issued in half the time; otherwise one warp per stage.
+    const int G = S <= 4 ? 2 : 1;
+    const int grp = G == 2 ? warp >> 1 : warp, sub = G == 2 ? (warp & 1) : 0;
+    const int PA = (kProducerWarps / G) < S ? (kProducerWarps / G) : S;   // owner groups (<= stages: a waiter may be one phase behind at most)
+    const uint32_t lane0 = (lane == 0 && sub == 0) ? 1u : 0u;
 
     auto load_table = [&](int64_t work, int (&regs)[kTableRegs]) {
       const int64_t tm = work / p.n_tiles_n;
@@ -151,7 +165,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       }
     };
 
-    uint32_t st = 0, ph = 0;                   // stage being filled, parity of its empty barrier
+    uint32_t st = grp, ph = 0;                 // stage / parity of this group's next owned iteration
+    int own_skip = grp < PA ? grp : 0x7fffffff;     // iterations until the next owned one
     uint32_t tile_seq = 0;
 #ifdef GCD_TC_PROFILE
     long long prof_wait = 0, prof_iters = 0, prof_table = 0; const long long prof_t0 = clock64();
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #ifdef GCD_TC_PROFILE
       const long long ct0 = clock64();
 #endif
-      named_bar_sync(1, kProducerThreads + 32);  // previous tile's table no longer needed by anyone (weight warp included)
+      named_bar_sync(1, kProducerThreads);     // previous tile's table no longer needed by any owner
       uint32_t my_mask = 0;
 #pragma unroll
       for (int i = 0; i < kTableRegs; ++i) {
@@ -173,13 +188,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
         }
       }
       if (lane == 0) s_any[warp] = my_mask;
-      named_bar_sync(1, kProducerThreads + 32);
+      named_bar_sync(1, kProducerThreads);
       if (work + gridDim.x < n_work) load_table(work + gridDim.x, table);   // prefetch: consumed at the next tile start
       uint32_t mask = 0, lo_mask;
 #pragma unroll
       for (int w = 0; w < kProducerWarps; ++w) mask |= s_any[w];
       if (t == 0) s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
       rotate(mask, mask, lo_mask);
+      const uint8_t* w_tile = p.w_packed + (int64_t)(work % p.n_tiles_n) * p.n_tile_cols * kRowBytes;
 #ifdef GCD_TC_PROFILE
       prof_table += clock64() - ct0;
 #endif
@@ -188,69 +204,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
         if (mask == 0) { mask = lo_mask; lo_mask = 0; }
-        const int* nb = s_nbr + k * kTileM + row0;
-        const int i0 = nb[0], i1 = nb[32], i2 = nb[64], i3 = nb[96];
-        const char* s0 = col_base + (int64_t)max(i0, 0) * ld_bytes;
-        const char* s1 = col_base + (int64_t)max(i1, 0) * ld_bytes;
-        const char* s2 = col_base + (int64_t)max(i2, 0) * ld_bytes;
-        const char* s3 = col_base + (int64_t)max(i3, 0) * ld_bytes;
-        const uint32_t n0 = i0 >= 0 ? 16u : 0u, n1 = i1 >= 0 ? 16u : 0u, n2 = i2 >= 0 ? 16u : 0u, n3 = i3 >= 0 ? 16u : 0u;
 #pragma unroll
         for (int q = 0; q < (kNQ ? kNQ : 8); ++q) {
           if (!kNQ && q >= nq) break;
+          if (own_skip != 0) { --own_skip; continue; }
+          own_skip = PA - 1;
 #ifdef GCD_TC_PROFILE
           const long long cw0 = clock64();
 #endif
           mbar_wait_addr(empty0 + st * 8, ph ^ 1);
 #ifdef GCD_TC_PROFILE
           prof_wait += clock64() - cw0; ++prof_iters;
+          const uint32_t wb = (p.ablate & 4) ? 16u : b_bytes;
+#else
+          const uint32_t wb = b_bytes;
+#endif
+          // weight slice of (k, q): one bulk copy, its bytes join the stage's transaction count
+          mbar_arrive_expect_tx_pred(&full_bar[st], wb, lane0);
+          bulk_g2s_pred(b_base + st * b_bytes, w_tile + ((int64_t)k * nq + q) * p.c_out * kRowBytes, wb, &full_bar[st], lane0);
+#ifdef GCD_TC_PROFILE
+          if (!(p.ablate & 2))
 #endif
           if (q + 1 < nq || last_active) {
+            const int* nb = s_nbr + k * kTileM + rsub;
             const uint32_t a_stage = a_base + st * kABytes;
-            cp_async_16(a_stage, s0 + q * (kChunkK * 2), n0);
-            cp_async_16(a_stage + 4096, s1 + q * (kChunkK * 2), n1);
-            cp_async_16(a_stage + 8192, s2 + q * (kChunkK * 2), n2);
-            cp_async_16(a_stage + 12288, s3 + q * (kChunkK * 2), n3);
+            const char* src_q = col_base + q * (kChunkK * 2);
+#pragma unroll
+            for (int jb = 0; jb < 32; jb += 8) {
+              if (G == 2 && (jb >> 4) != sub) continue;
+              int r[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r[j] = nb[(jb + j) * 4];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int jj = jb + j;
+                cp_async_16(a_stage + (jj >> 1) * 1024 + ((jj & 1) ? d_odd : d_even), src_q + (int64_t)max(r[j], 0) * ld_bytes, r[j] >= 0 ? 16u : 0u);
+              }
+            }
           }
-          cp_async_mbar_arrive_noinc_addr(full0 + st * 8);   // arrives when this thread's copies have landed
-          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
+          cp_async_mbar_arrive_noinc_addr(full0 + st * 8);   // arrives when this lane's copies have landed
+          st += PA;
+          if (st >= (uint32_t)S) { st -= S; ph ^= 1; }
         }
       }
     }
     cp_async_wait_all();                                 // nothing may still be writing smem at exit
 #ifdef GCD_TC_PROFILE
-    if (p.dbg && t == 32) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; }
+    if (p.dbg && t == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; }
 #endif
-  } else if (warp == kWeightWarp) {
-    // ===================================================================== weight producer (TMA bulk copies)
-    // Walks the same (tile, offset, slice) sequence as the gather warps and, per stage, posts the transaction
-    // count and one bulk copy of the pre-packed [n_tile_cols x 64] weight image.
-    const bool leader = elect_one();
-    const uint32_t b_base = smem_u32(smem + L.b_off);
-    const uint32_t b_bytes = L.b_bytes;
-    uint32_t st = 0, ph = 0;
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
-      const int tn = (int)(work % p.n_tiles_n);
-      named_bar_sync(1, kProducerThreads + 32);
-      named_bar_sync(1, kProducerThreads + 32);
-      uint32_t mask = 0, lo_mask;
-#pragma unroll
-      for (int w = 0; w < kProducerWarps; ++w) mask |= s_any[w];
-      rotate(mask, mask, lo_mask);
-      const uint8_t* w_tile = p.w_packed + (int64_t)tn * p.n_tile_cols * kRowBytes;
-      while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        if (mask == 0) { mask = lo_mask; lo_mask = 0; }
-        const uint8_t* w_k = w_tile + (int64_t)k * nq * p.c_out * kRowBytes;
-        for (int q = 0; q < nq; ++q) {
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_arrive_expect_tx_pred(&full_bar[st], b_bytes, leader ? 1u : 0u);
-          bulk_g2s_pred(b_base + st * b_bytes, w_k + (int64_t)q * p.c_out * kRowBytes, b_bytes, &full_bar[st], leader ? 1u : 0u);
-          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
-        }
-      }
-    }
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
     // The whole warp runs the loop with warp-uniform values (so descriptors live in uniform registers and there is
@@ -258,11 +259,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     const uint32_t idesc = make_idesc_bf16((uint32_t)p.n_tile_cols, 0, 0);
     const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem + L.a_off), 16, 1024);
     const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem + L.b_off), 16, 1024);
-    const uint64_t da_step = kABytes >> 4, db_step = L.b_bytes >> 4;      // descriptor address units are 16 bytes
+    const uint32_t da_step = kABytes >> 4, db_step = L.b_bytes >> 4;      // descriptor address units are 16 bytes
+    const uint32_t desc_hi = (uint32_t)(da0 >> 32);                        // identical for both operands (same layout / LBO / SBO)
+    const uint32_t da0_lo = (uint32_t)da0, db0_lo = (uint32_t)db0;
     const int last_ksteps = last_width / 16;
     const bool leader = elect_one();
     uint32_t st = 0, ph = 0, tile_seq = 0;
-    uint64_t da = da0, db = db0;
+    uint32_t da = da0_lo, db = db0_lo;
 #ifdef GCD_TC_PROFILE
     long long prof_full = 0, prof_acc = 0; const long long prof_t0 = clock64();
 #endif
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       const uint32_t tmem_d = tmem_base + buf * kAccStride;
       int n_iters = 1, q = 0;
       uint32_t accumulate = 0;
-      for (int it = 0; it < n_iters; ++it) {
+      for (int it = 0;;) {
 #ifdef GCD_TC_PROFILE
         const long long cf0 = clock64();
 #endif
@@ -293,18 +296,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
         // predicated issue slots (no branch: divergence + reconvergence around an elected lane costs ~230 cycles per stage)
 #pragma unroll
         for (int ks = 0; ks < kChunkK / 16; ++ks)
-          mma_bf16_ss_pred(tmem_d, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, accumulate | (uint32_t)ks, (leader && ks < ksteps) ? 1u : 0u);
+#ifdef GCD_TC_PROFILE
+          mma_bf16_ss_pred_lo(tmem_d, da + (uint32_t)(ks * 2), db + (uint32_t)(ks * 2), desc_hi, idesc, accumulate | (uint32_t)ks, (leader && ks < ksteps && !(p.ablate & 1)) ? 1u : 0u);
+#else
+          mma_bf16_ss_pred_lo(tmem_d, da + (uint32_t)(ks * 2), db + (uint32_t)(ks * 2), desc_hi, idesc, accumulate | (uint32_t)ks, (leader && ks < ksteps) ? 1u : 0u);
+#endif
         mma_commit_pred(&empty_bar[st], leader ? 1u : 0u);
         accumulate = 1;
         if (++q == nq) q = 0;
-        if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0; db = db0; } else { da += da_step; db += db_step; }
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0_lo; db = db0_lo; } else { da += da_step; db += db_step; }
+        ++it;
+        if (__all_sync(0xffffffffu, it >= n_iters)) break;      // warp vote: the exit is a uniform branch, loop state stays in uniform registers
       }
       mma_commit_pred(&tmem_full[buf], leader ? 1u : 0u);
     }
 #ifdef GCD_TC_PROFILE
     if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[4] = clock64() - prof_t0; d[5] = prof_full; d[6] = prof_acc; }
 #endif
-  } else {
+  } else if (warp < kMmaWarp) {
     // ===================================================================== epilogue
     const int ew = warp - kEpilogueWarp0;      // == warp % 4: the TMEM lane quarter this warp may read
     uint32_t tile_seq = 0;
@@ -646,6 +655,13 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.n_tiles_n = (a->c_out + 255) / 256;
   p.n_tile_cols = a->c_out / p.n_tiles_n;
   if (p.n_tile_cols % 16 != 0 || p.n_tile_cols * p.n_tiles_n != a->c_out) { set_error("conv_forward_tc: cannot split %d output channels into equal tiles", a->c_out); return GCD_ERR_UNSUPPORTED; }
+  // Deep levels have fewer row tiles than SMs and the kernel is bound by each SM's shared-memory bandwidth
+  // (per stage 2 x (16 KB of rows + n_tile_cols x 128 B of weights) through a 128 B/clk port), so idle SMs are put to work
+  // by splitting the output channels further: every CTA then streams a narrower weight slice.
+  {
+    const int64_t tiles_m = ceil_div(a->n_out, kTileM);
+    while (tiles_m * p.n_tiles_n * 2 <= kNumSMs && p.n_tile_cols % 32 == 0 && p.n_tile_cols / 2 >= 32) { p.n_tiles_n *= 2; p.n_tile_cols /= 2; }
+  }
   p.w_packed = (const uint8_t*)a->w_packed;  // offset mirroring (dgrad of stride-1 maps) is baked into the packed image
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
@@ -656,6 +672,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.stages = stages;
 #ifdef GCD_TC_PROFILE
   p.dbg = g_debug_buffer;
+  p.ablate = getenv("GCD_TC_ABLATE") ? atoi(getenv("GCD_TC_ABLATE")) : 0;
 #endif
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;

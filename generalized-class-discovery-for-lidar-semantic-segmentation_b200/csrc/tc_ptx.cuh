@@ -140,6 +140,20 @@ __device__ __forceinline__ void mma_bf16_ss_pred(uint32_t tmem_d, uint64_t desc_
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred)
       : "memory");
 }
+// Same, descriptors given as (low word, shared high word): the high word (LBO / SBO / layout bits) never changes, only the
+// 14-bit start-address field in the low word does, so the issuing warp carries two 32-bit values instead of two 64-bit ones.
+__device__ __forceinline__ void mma_bf16_ss_pred_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                    uint32_t accumulate, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(pred)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_pred(uint64_t* bar, uint32_t pred) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

@@ -1,23 +1,24 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel name."""
-import csv, sys, re, collections
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel (template arguments kept)."""
+import collections
+import csv
+import re
+import sys
+
 path = sys.argv[1]
-rows = []
-with open(path, newline="") as f:
-    lines = [l for l in f if not l.startswith("==")]
-rd = csv.DictReader(lines)
+steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0       # optional: number of training steps the list covers
+lines = [l for l in open(path, newline="") if not l.startswith("==")]
 tot = collections.defaultdict(lambda: [0.0, 0])
-for r in rd:
+for r in csv.DictReader(lines):
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    name = r["Kernel Name"].replace("(anonymous namespace)::", "")
-    name = re.sub(r"\(.*", "", name)
+    name = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", r["Kernel Name"])
     name = re.sub(r"^void ", "", name)
-    name = re.sub(r"<.*", "", name)
-    v = float(r["Metric Value"].replace(",", ""))
-    unit = r.get("Metric Unit", "ns")
-    v = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}.get(unit, 1e-3)
-    tot[name][0] += v; tot[name][1] += 1
+    m = re.match(r"([\w:]+)(<[^(]*>)?\(", name)
+    short = (m.group(1) + (m.group(2) or "") if m else name)[:72]
+    v = float(r["Metric Value"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r.get("Metric Unit", "ns"), 1e-3)
+    tot[short][0] += v
+    tot[short][1] += 1
 total = sum(v[0] for v in tot.values())
-print(f"total {total/1e3:.3f} ms over {sum(v[1] for v in tot.values())} launches")
-for name, (us, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:40]:
-    print(f"{us/total*100:6.2f}%  {us/1e3:9.3f} ms  {n:6d} launches  {us/n:9.2f} us/launch  {name}")
+print(f"total {total / 1e3:.3f} ms over {sum(v[1] for v in tot.values())} launches ({total / 1e3 / steps:.3f} ms per step over {steps:g} steps)")
+for name, (us, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:45]:
+    print(f"{us / total * 100:6.2f}%  {us / 1e3 / steps:8.3f} ms/step  {n:5d} launches  {us / n:8.2f} us/launch  {name}")

@@ -57,6 +57,7 @@ struct FwdParams {
   const float* bias;
   void* out; int64_t ld_out; int out_is_bf16;
   int stages;
+  int group;                       // producer warps that share one stage (1, 2, 4, 8)
 #ifdef GCD_TC_PROFILE
   long long* dbg;
   int ablate;                      // profile build only: 1 = no MMA issue, 2 = no gather copies, 4 = weight copies of 16 B
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 
   if (threadIdx.x == 0) {
     // full: one completion-triggered arrival per lane of the owning producer warp + its lane 0's arrive.expect_tx (weights)
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], (S <= 4 ? 64 : 32) + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 32 * p.group + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     fence_mbar_init();
   }
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
     // Few, fat stages (wide N tiles: S <= 4): two warps share a stage (16 rows per lane each) so that all eight warps
     // stay busy and a stage is issued in half the time; otherwise one warp per stage.
-    const int G = S <= 4 ? 2 : 1;
-    const int grp = G == 2 ? warp >> 1 : warp, sub = G == 2 ? (warp & 1) : 0;
+    const int G = p.group;                     // warps per stage: 1, 2, 4 or 8
+    const int grp = warp / G, sub = warp % G;
     const int PA = (kProducerWarps / G) < S ? (kProducerWarps / G) : S;   // owner groups (<= stages: a waiter may be one phase behind at most)
     const uint32_t lane0 = (lane == 0 && sub == 0) ? 1u : 0u;
 
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
             const char* src_q = col_base + q * (kChunkK * 2);
 #pragma unroll
             for (int jb = 0; jb < 32; jb += 8) {
-              if (G == 2 && (jb >> 4) != sub) continue;
+              if (((jb >> 3) * G) >> 2 != sub) continue;     // the warp's share of the rows: 32 / G per lane
               int r[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) r[j] = nb[(jb + j) * 4];
@@ -670,6 +671,8 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   if (const char* e = getenv("GCD_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));   // tuning aid
   if (stages < 2) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
+  p.group = stages <= 4 ? 2 : 1;      // measured: one warp per stage is best with >= 5 stages, a warp pair when the stages are few and fat
+  if (const char* e = getenv("GCD_TC_GROUP")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) p.group = g; }   // tuning aid
 #ifdef GCD_TC_PROFILE
   p.dbg = g_debug_buffer;
   p.ablate = getenv("GCD_TC_ABLATE") ? atoi(getenv("GCD_TC_ABLATE")) : 0;

@@ -75,6 +75,11 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
+// predicated form (per-lane predicate, no branch)
+__device__ __forceinline__ void cp_async_16_pred(uint32_t dst_smem, const void* src, uint32_t src_bytes, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}"
+               ::"r"(dst_smem), "l"(src), "r"(src_bytes), "r"(pred) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>

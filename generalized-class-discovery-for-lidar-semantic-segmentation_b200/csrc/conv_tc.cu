@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     fence_mbar_init();
     int cum = 0;
@@ -482,65 +482,83 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
   };
 
   if (warp < kProducerWarps) {
-    // ===================================================================== producers
-    const int chunk16 = lane & 7;
-    const int row0 = warp * 4 + (lane >> 3);                                 // this thread's pairs of a stage: row0, row0 + 32
-    const uint32_t doff0 = row0 * kRowBytes + ((chunk16 ^ (row0 & 7)) << 4);
+    // ===================================================================== producers (stage owners, see conv_fwd_tc_kernel)
+    // Warp w owns the ring slots of stages g == w (mod PA): it gathers the 64 pairs of the stage itself (input rows: up to two
+    // 64-channel slabs, gradient rows: kGS slabs; 16 rows x (2 + kGS) 16-byte copies per lane).  Its next stage is PA stages
+    // away, so the pair indices of that stage are fetched from global memory while this one is being issued: the index
+    // latency, which paced the lock-step version (one stage of lookahead), is hidden behind PA - 1 other stages.
+    const int chunk16 = lane & 7, rsub = lane >> 3;                          // this lane's pairs of a stage: rsub + 4 j, j = 0..15
+    const uint32_t d_even = rsub * kRowBytes + ((chunk16 ^ rsub) << 4);
+    const uint32_t d_odd = (rsub + 4) * kRowBytes + ((chunk16 ^ (rsub + 4)) << 4);
     const int64_t lda = p.ld_in * 2, ldg = p.ld_g * 2;                       // bytes
-    const uint32_t stage0 = smem_u32(smem) + doff0;
+    const uint32_t stage0 = smem_u32(smem);
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
     uint32_t g_on = 0;                                                       // bit s: this thread's chunk exists in gradient slab s
 #pragma unroll
     for (int s = 0; s < kGS; ++s) g_on |= (s * 64 + chunk16 * 8 < p.c_out ? 1u : 0u) << s;
     const char* g_col = reinterpret_cast<const char*>(p.gout + chunk16 * 8);
-    uint32_t st = 0, ph = 0;
+    const int PA = S < kProducerWarps ? S : kProducerWarps;
+    uint32_t st = warp, ph = 0;
+    int64_t own_skip = warp < PA ? warp : (int64_t)1 << 60;                  // stages until this warp's next owned one
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
       int k, mt; int64_t p_begin, p_end;
       decode(work, k, p_begin, p_end, mt);
+      const int64_t n_stages = (p_end - p_begin + kWgPairs - 1) / kWgPairs;
+      if (own_skip >= n_stages) { own_skip -= n_stages; continue; }          // nothing of this item belongs to the warp
       const int c_base = mt * 128;
       const char* a_col = reinterpret_cast<const char*>(p.in + c_base + chunk16 * 8);
       const bool a_on0 = c_base + chunk16 * 8 < p.c_in, a_on1 = c_base + 64 + chunk16 * 8 < p.c_in;
-      // software pipeline: the pair indices of the next stage are fetched while this stage's copies are issued
-      int ri0, ri1, ro0, ro1;
-      auto fetch = [&](int64_t p0) {
-        const int64_t pa = p0 + row0, pb = pa + 32;
-        ri0 = ro0 = ri1 = ro1 = -1;
-        if (pa < p_end) { ri0 = p.pair_in ? __ldg(&p.pair_in[pa]) : (int)pa; ro0 = p.pair_out ? __ldg(&p.pair_out[pa]) : (int)pa; }
-        if (pb < p_end) { ri1 = p.pair_in ? __ldg(&p.pair_in[pb]) : (int)pb; ro1 = p.pair_out ? __ldg(&p.pair_out[pb]) : (int)pb; }
+      int ri[16], ro[16];
+      auto fetch = [&](int64_t p0, int (&fi)[16], int (&fo)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t pa = p0 + rsub + 4 * j;
+          fi[j] = fo[j] = -1;
+          if (pa < p_end) { fi[j] = p.pair_in ? __ldg(&p.pair_in[pa]) : (int)pa; fo[j] = p.pair_out ? __ldg(&p.pair_out[pa]) : (int)pa; }
+        }
       };
-      fetch(p_begin);
-      for (int64_t p0 = p_begin; p0 < p_end; p0 += kWgPairs) {
-        const char* sa0 = a_col + (int64_t)max(ri0, 0) * lda;
-        const char* sa1 = a_col + (int64_t)max(ri1, 0) * lda;
-        const char* sg0 = g_col + (int64_t)max(ro0, 0) * ldg;
-        const char* sg1 = g_col + (int64_t)max(ro1, 0) * ldg;
-        const uint32_t n0 = ri0 >= 0 ? 16u : 0u, n1 = ri1 >= 0 ? 16u : 0u;
-        if (p0 + kWgPairs < p_end) fetch(p0 + kWgPairs);
+      int64_t it = own_skip;
+      fetch(p_begin + it * kWgPairs, ri, ro);
+      for (; it < n_stages; it += PA) {
+        int ni[16], no[16];
+        const bool more = it + PA < n_stages;
+        if (more) fetch(p_begin + (it + PA) * kWgPairs, ni, no);
         mbar_wait_addr(empty0 + st * 8, ph ^ 1);
         const uint32_t a_stage = stage0 + st * stage_bytes;
-        if (a_on0) { cp_async_16(a_stage, sa0, n0); cp_async_16(a_stage + 4096, sa1, n1); }
-        if (a_on1) { cp_async_16(a_stage + kSlabBytes, sa0 + 128, n0); cp_async_16(a_stage + kSlabBytes + 4096, sa1 + 128, n1); }
 #pragma unroll
-        for (int s = 0; s < kGS; ++s)
-          if (g_on & (1u << s)) {
-            cp_async_16(a_stage + (2 + s) * kSlabBytes, sg0 + s * 128, n0);
-            cp_async_16(a_stage + (2 + s) * kSlabBytes + 4096, sg1 + s * 128, n1);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t off = (j >> 1) * 1024 + ((j & 1) ? d_odd : d_even);
+          const uint32_t n = ri[j] >= 0 ? 16u : 0u;
+          const char* sa = a_col + (int64_t)max(ri[j], 0) * lda;
+          const char* sg = g_col + (int64_t)max(ro[j], 0) * ldg;
+          if (a_on0) cp_async_16(a_stage + off, sa, n);
+          if (a_on1) cp_async_16(a_stage + kSlabBytes + off, sa + 128, n);
+#pragma unroll
+          for (int s = 0; s < kGS; ++s)
+            if (g_on & (1u << s)) cp_async_16(a_stage + (2 + s) * kSlabBytes + off, sg + s * 128, n);
+        }
         cp_async_mbar_arrive_noinc_addr(full0 + st * 8);
-        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
+        st += PA;
+        if (st >= (uint32_t)S) { st -= S; ph ^= 1; }
+        if (more) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { ri[j] = ni[j]; ro[j] = no[j]; }
+        }
       }
+      own_skip = it - n_stages;
     }
     cp_async_wait_all();
   } else if (warp == kMmaWarp) {
-    // ===================================================================== MMA issuer (warp-uniform, elected lane issues)
+    // ===================================================================== MMA issuer (uniform loop, elected lane issues)
     {
       const uint32_t idesc = make_idesc_bf16((uint32_t)p.c_out, 1, 1);   // both operands MN-major
       const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem), kSlabBytes, 1024);
       const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem) + 2 * kSlabBytes, kSlabBytes, 1024);
-      const uint64_t stage_step = stage_bytes >> 4, k_step = (16 * kRowBytes) >> 4;
+      const uint32_t desc_hi = (uint32_t)(da0 >> 32), da0_lo = (uint32_t)da0, db0_lo = (uint32_t)db0;
+      const uint32_t stage_step = stage_bytes >> 4, k_step = (16 * kRowBytes) >> 4;
       const bool leader = elect_one();
       uint32_t st = 0, ph = 0, seq = 0;
-      uint64_t da = da0, db = db0;
+      uint32_t da = da0_lo, db = db0_lo;
       for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++seq) {
         int k, mt; int64_t p_begin, p_end;
         decode(work, k, p_begin, p_end, mt);
@@ -550,15 +568,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
         const uint32_t tmem_d = tmem_base + buf * kAccStride;
         const int n_stages = (int)((p_end - p_begin + kWgPairs - 1) / kWgPairs);
         uint32_t accumulate = 0;
-        for (int it = 0; it < n_stages; ++it) {
+        for (int it = 0;;) {
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < kWgPairs / 16; ++ks)
-            mma_bf16_ss_pred(tmem_d, da + ks * k_step, db + ks * k_step, idesc, accumulate | (uint32_t)ks, leader ? 1u : 0u);
+            mma_bf16_ss_pred_lo(tmem_d, da + ks * k_step, db + ks * k_step, desc_hi, idesc, accumulate | (uint32_t)ks, leader ? 1u : 0u);
           mma_commit_pred(&empty_bar[st], leader ? 1u : 0u);
           accumulate = 1;
-          if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0; db = db0; } else { da += stage_step; db += stage_step; }
+          if (++st == (uint32_t)S) { st = 0; ph ^= 1; da = da0_lo; db = db0_lo; } else { da += stage_step; db += stage_step; }
+          ++it;
+          if (__all_sync(0xffffffffu, it >= n_stages)) break;     // warp vote: uniform exit keeps the loop state in uniform registers
         }
         mma_commit_pred(&tmem_full[buf], leader ? 1u : 0u);
       }
@@ -582,7 +602,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
         tmem_ld_wait();
         if (c < p.c_in) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + n0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; j += 4)      // dst + n0 is 16-byte aligned (c_out % 16 == 0): one vector reduction per 4 columns
+            red_add_v4_f32(dst + n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
       }
       tc_fence_before();

@@ -110,6 +110,11 @@ __device__ __forceinline__ void bulk_g2s_pred(uint32_t dst_smem, const void* src
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "r"(pred) : "memory");
 }
 
+// 16-byte vector reduction (sm_90+): four fp32 adds in one L2 operation
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp

@@ -182,6 +182,7 @@ def run_ours(args):
     import MinkowskiEngine as ME
     from gcdlss_b200 import ops, synth
     from gcdlss_b200.ddp import GradBucketReducer
+    from gcdlss_b200.steps import point_cross_entropy
     from models.multiheadminkunet import MinkUNetBase
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,7 +223,7 @@ def run_ours(args):
         else:
             reducer.reset()                        # .grad are views of the flat all-reduce buckets: zero them in place
         out = model(st)
-        loss = torch.nn.functional.cross_entropy(out["logits"], labels)
+        loss = point_cross_entropy(out["logits"], labels)
         loss.backward()
         if reducer is not None:
             reducer.finish()

@@ -102,6 +102,14 @@ class _ConvBase(nn.Module):
                 w2 = torch.cat([w2, w2.new_zeros(k_pad - k_real, self.out_channels)], 0)
             ident = mgr.kernel_map(ts_out, 1, 1, False)
             out = SparseConvFunction.apply(col, w2, self.bias, ident, self._out_dtype(col, k_pad, 1))
+        elif (bf16 and self.kernel_volume == 1 and self.out_channels % 16 != 0 and feats.dtype == torch.bfloat16 and
+              ops.tc_supported(self.in_channels, (self.out_channels + 15) // 16 * 16, 1)):
+            # classifier head (ref models/minkunet.py:123-128, Cout = number of classes): zero-pad the output channels to
+            # the next multiple of 16 so forward, dgrad and wgrad run on the tensor cores; fp32 logits, padding sliced off
+            pad = (self.out_channels + 15) // 16 * 16 - self.out_channels
+            w_pad = torch.nn.functional.pad(self.kernel, (0, pad))
+            b_pad = torch.nn.functional.pad(self.bias, (0, pad)) if self.bias is not None else None
+            out = SparseConvFunction.apply(feats, w_pad, b_pad, kmap, torch.float32)[:, :self.out_channels]
         else:
             out_dtype = self._out_dtype(feats, self.in_channels, self.kernel_volume)
             if bf16 and out_dtype == torch.bfloat16 and feats.dtype != torch.bfloat16:

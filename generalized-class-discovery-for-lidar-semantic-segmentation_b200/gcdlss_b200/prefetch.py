@@ -30,7 +30,9 @@ class PreparedBatch:
 
 class BatchPrefetcher:
     def __init__(self, device=None, n_levels: int = 5, stem_kernel: int = 5, training: bool = True):
-        self.stream = torch.cuda.Stream(device=device)
+        # high priority: the build is a chain of small kernels with host reads in between (voxel counts per level); behind
+        # the training stream's persistent 148-CTA kernels each read would otherwise wait for a free SM slot
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.n_levels, self.stem_kernel, self.training = n_levels, stem_kernel, training
 
     def submit(self, make_inputs, wait_for_current_stream: bool = False) -> PreparedBatch:

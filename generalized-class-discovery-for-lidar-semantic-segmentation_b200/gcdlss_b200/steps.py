@@ -22,10 +22,20 @@ from .quantize import sparse_quantize_gpu
 from .sparse_tensor import SparseTensor
 
 
+def point_cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int | None = None) -> torch.Tensor:
+    """``F.cross_entropy(logits, labels, ignore_index=...)`` (mean over the counted points) through the per-point
+    kernels: torch's fused mean reduction is a single-block kernel (0.21 ms forward + 0.12 ms backward on 200 k points,
+    more than two of the sparse convolutions), the unreduced form plus a mean is a few microseconds."""
+    if ignore_index is None:
+        return F.cross_entropy(logits, labels, reduction="none").mean()
+    per_point = F.cross_entropy(logits, labels, reduction="none", ignore_index=ignore_index)
+    return per_point.sum() / (labels != ignore_index).sum().clamp(min=1)
+
+
 def stage1_step(model, feats, bcoords, labels):
     st = SparseTensor(features=feats.float(), coordinates=bcoords.int())
     out = model(st)
-    return F.cross_entropy(out["logits"], labels.long())
+    return point_cross_entropy(out["logits"], labels.long())
 
 
 def laser_mix(points_sup, points_unsup, feats_sup, feats_unsup, labels_sup, labels_unsup, num_areas: int,
@@ -72,7 +82,7 @@ class Stage2Harness:
             out_t = self.teacher(st)                                       # shares st's kernel maps with the student
         out_s = self.student(st)
         n_sup = sup["coords"].shape[0]
-        loss = F.cross_entropy(out_s["logits"][:n_sup], sup["labels"].long())
+        loss = point_cross_entropy(out_s["logits"][:n_sup], sup["labels"].long())
         prob_s = F.softmax(out_s["logits"][n_sup:], dim=1)
         prob_t = F.softmax(out_t["logits"][n_sup:], dim=1)
         loss = loss + F.mse_loss(prob_s, prob_t.detach()) * self.mse_coeff
@@ -104,7 +114,7 @@ class Stage2Harness:
         out_mix = self.student(mix_st)
         mix_labels = torch.cat(mixed_labels)[lm_umap]
         if bool((mix_labels >= 0).any()):
-            loss = loss + 0.1 * F.cross_entropy(out_mix["logits"], mix_labels.long(), ignore_index=-1)
+            loss = loss + 0.1 * point_cross_entropy(out_mix["logits"], mix_labels.long(), ignore_index=-1)
         else:
             loss = loss + 0.0 * out_mix["logits"].sum()
         if self.reducer is not None:

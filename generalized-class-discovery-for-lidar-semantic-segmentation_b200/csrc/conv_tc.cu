@@ -38,6 +38,7 @@ constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
 constexpr int kEpilogueWarp0 = kProducerWarps;        // 8: (8 + i) % 4 == i, the TMEM lane quarter rule
 constexpr int kMmaWarp = kProducerWarps + 4;          // 12
+constexpr int kTableWarp = kProducerWarps + 5;        // 13 (forward kernel: stages the neighbour-table slices)
 constexpr int kTcThreads = kProducerThreads + kEpilogueThreads + 64;
 constexpr int kMaxKV = 27;
 constexpr int kMaxStages = 8;
@@ -45,7 +46,6 @@ constexpr int kTileRing = 16;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM columns between the two accumulator buffers
 constexpr int kSmemBudget = 226 * 1024;
-constexpr int kTableRegs = (kMaxKV + 1) / 2;                    // table entries a producer thread prefetches per tile
 
 struct FwdParams {
   const __nv_bfloat16* in; int64_t ld_in;
@@ -74,7 +74,7 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
   L.a_off = 0;
   L.b_off = L.a_off + (uint32_t)stages * kABytes;
   L.nbr_off = L.b_off + (uint32_t)stages * L.b_bytes;
-  L.bar_off = L.nbr_off + kMaxKV * kTileM * 4;
+  L.bar_off = L.nbr_off + 2 * kMaxKV * kTileM * 4;     // two table buffers (tile t and t + 1)
   L.total = L.bar_off + 512;
   return L;
 }
@@ -88,15 +88,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
   // dynamic smem base is at least 16-byte aligned; the swizzle pattern needs 1024.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const SmemLayout L = make_layout(p.stages, p.n_tile_cols);
-  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem + L.nbr_off);            // [kv][128]
+  int32_t* s_nbr0 = reinterpret_cast<int32_t*>(smem + L.nbr_off);           // [2][kv][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* full_bar = bars;                    // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;      // [kMaxStages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* s_tmem_base = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint32_t* s_any = s_tmem_base + 1;            // [kProducerWarps] per-producer-warp offset masks
-  int32_t* s_iters = reinterpret_cast<int32_t*>(s_any + kProducerWarps);  // [kTileRing]
+  uint64_t* table_ready = tmem_empty + 2;       // [2] table buffer b holds the complete slice of its tile (table warp -> producers)
+  uint64_t* table_free = table_ready + 2;       // [2] every producer warp is done reading buffer b
+  uint32_t* s_tmem_base = reinterpret_cast<uint32_t*>(table_free + 2);
+  uint32_t* s_mask = s_tmem_base + 1;           // [2] offsets with at least one hit in the tile of buffer b
+  int32_t* s_iters = reinterpret_cast<int32_t*>(s_mask + 2);  // [kTileRing]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     // full: one completion-triggered arrival per lane of the owning producer warp + its lane 0's arrive.expect_tx (weights)
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 32 * p.group + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&table_ready[b], 1); mbar_init(&table_free[b], kProducerWarps); }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
@@ -133,9 +136,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     // lane), then hands the stage over with completion-triggered arrivals.  Up to PA stages are being filled at once
     // and the per-stage fixed costs (barrier wait, index loads, arrive, loop control) are paid by one warp instead of
     // by all eight in lock-step -- measured (tools/ubench/ldgsts_gather.cu): 270 -> ~130 cycles per stage.
-    const int t = threadIdx.x;                 // 0..255
-    const int trow = t & (kTileM - 1);         // tile row this thread loads table entries for
-    const int tpar = t >> 7;                   // ... for offsets k = tpar, tpar + 2, ...
     const int chunk = lane & 7;
     const int rsub = lane >> 3;                // this lane's rows are rsub + 4 j, j = 0..31
     const uint32_t d_even = rsub * kRowBytes + ((chunk ^ rsub) << 4);                 // j even: row & 7 == rsub
@@ -154,47 +154,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     const int PA = (kProducerWarps / G) < S ? (kProducerWarps / G) : S;   // owner groups (<= stages: a waiter may be one phase behind at most)
     const uint32_t lane0 = (lane == 0 && sub == 0) ? 1u : 0u;
 
-    auto load_table = [&](int64_t work, int (&regs)[kTableRegs]) {
-      const int64_t tm = work / p.n_tiles_n;
-      const int64_t r = tm * kTileM + trow;
-#pragma unroll
-      for (int i = 0; i < kTableRegs; ++i) {
-        const int k = 2 * i + tpar;
-        int v = -1;
-        if (k < p.kv && r < p.n_out) v = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.n_out + r]) : (int)r;
-        regs[i] = v;
-      }
-    };
-
     uint32_t st = grp, ph = 0;                 // stage / parity of this group's next owned iteration
     int own_skip = grp < PA ? grp : 0x7fffffff;     // iterations until the next owned one
     uint32_t tile_seq = 0;
 #ifdef GCD_TC_PROFILE
     long long prof_wait = 0, prof_iters = 0, prof_table = 0; const long long prof_t0 = clock64();
 #endif
-    int table[kTableRegs];
-    if ((int64_t)blockIdx.x < n_work) load_table(blockIdx.x, table);
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
 #ifdef GCD_TC_PROFILE
       const long long ct0 = clock64();
 #endif
-      named_bar_sync(1, kProducerThreads);     // previous tile's table no longer needed by any owner
-      uint32_t my_mask = 0;
-#pragma unroll
-      for (int i = 0; i < kTableRegs; ++i) {
-        const int k = 2 * i + tpar;
-        if (k < p.kv) {
-          s_nbr[k * kTileM + trow] = table[i];
-          if (__any_sync(0xffffffffu, table[i] >= 0)) my_mask |= 1u << k;
-        }
-      }
-      if (lane == 0) s_any[warp] = my_mask;
-      named_bar_sync(1, kProducerThreads);
-      if (work + gridDim.x < n_work) load_table(work + gridDim.x, table);   // prefetch: consumed at the next tile start
-      uint32_t mask = 0, lo_mask;
-#pragma unroll
-      for (int w = 0; w < kProducerWarps; ++w) mask |= s_any[w];
-      if (t == 0) s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
+      // the table warp stages the slice one tile ahead: no producer-wide synchronisation at tile boundaries, a warp
+      // that has issued its last stage of tile t goes straight on to its first stage of tile t + 1
+      const uint32_t tb = tile_seq & 1;
+      mbar_wait(&table_ready[tb], (tile_seq >> 1) & 1);
+      const int32_t* s_nbr = s_nbr0 + tb * (kMaxKV * kTileM);
+      uint32_t mask = s_mask[tb], lo_mask;
       rotate(mask, mask, lo_mask);
       const uint8_t* w_tile = p.w_packed + (int64_t)(work % p.n_tiles_n) * p.n_tile_cols * kRowBytes;
 #ifdef GCD_TC_PROFILE
@@ -248,11 +223,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
           if (st >= (uint32_t)S) { st -= S; ph ^= 1; }
         }
       }
+      mbar_arrive_pred(&table_free[tb], lane == 0 ? 1u : 0u);     // this warp has read everything it needs from buffer tb
     }
     cp_async_wait_all();                                 // nothing may still be writing smem at exit
 #ifdef GCD_TC_PROFILE
-    if (p.dbg && t == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; }
+    if (p.dbg && threadIdx.x == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; }
 #endif
+  } else if (warp == kTableWarp) {
+    // ===================================================================== table warp
+    // Stages the [kv][128] slice of the neighbour table of tile t + 1 while tile t is being processed (two buffers), works
+    // out which offsets have a hit in the tile and publishes the tile's iteration count for the MMA warp.
+    uint32_t tile_seq = 0;
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+      const uint32_t tb = tile_seq & 1;
+      if (tile_seq >= 2) mbar_wait(&table_free[tb], ((tile_seq - 2) >> 1) & 1);
+      int32_t* dst = s_nbr0 + tb * (kMaxKV * kTileM);
+      const int64_t r0 = (work / p.n_tiles_n) * kTileM + lane;
+      uint32_t mask = 0;
+      for (int kb = 0; kb < p.kv; kb += 14) {             // 56 loads in flight per lane (a load per k would cost a memory latency each)
+        int v[14][4];
+#pragma unroll
+        for (int kk = 0; kk < 14; ++kk) {
+          const int k = kb + kk;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t r = r0 + 32 * j;
+            v[kk][j] = -1;
+            if (k < p.kv && r < p.n_out) v[kk][j] = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.n_out + r]) : (int)r;
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 14; ++kk) {
+          const int k = kb + kk;
+          if (k < p.kv) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[k * kTileM + lane + 32 * j] = v[kk][j];
+            if (__any_sync(0xffffffffu, (v[kk][0] & v[kk][1] & v[kk][2] & v[kk][3]) >= 0)) mask |= 1u << k;     // some entry is not -1
+          }
+        }
+      }
+      if (lane == 0) {
+        s_mask[tb] = mask;
+        s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
+      }
+      __syncwarp();
+      mbar_arrive_pred(&table_ready[tb], lane == 0 ? 1u : 0u);
+    }
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
     // The whole warp runs the loop with warp-uniform values (so descriptors live in uniform registers and there is
@@ -687,7 +703,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.w_packed = (const uint8_t*)a->w_packed;  // offset mirroring (dgrad of stride-1 maps) is baked into the packed image
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
-  int stages = (kSmemBudget - 1024 - kMaxKV * kTileM * 4 - 512) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - 2 * kMaxKV * kTileM * 4 - 512) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   if (const char* e = getenv("GCD_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));   // tuning aid
   if (stages < 2) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }

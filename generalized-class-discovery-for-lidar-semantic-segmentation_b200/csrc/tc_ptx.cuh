@@ -100,6 +100,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 }
 
 // predicated forms for the elected lane of a converged warp (no branch, see mma_bf16_ss_pred)
+__device__ __forceinline__ void mbar_arrive_pred(uint64_t* bar, uint32_t pred) {
+  asm volatile("{\n\t.reg .b64 st;\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q mbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
+               ::"r"(smem_u32(bar)), "r"(pred) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx_pred(uint64_t* bar, uint32_t bytes, uint32_t pred) {
   asm volatile("{\n\t.reg .b64 st;\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
                ::"r"(smem_u32(bar)), "r"(bytes), "r"(pred) : "memory");

@@ -19,5 +19,10 @@ w = torch.randn(27, cin, cout, device=dev) * 0.05
 packed = ops.pack_weights(w, False, False)
 for _ in range(4):
     ops.conv_forward(x, km.nbr, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=packed)
+g = torch.randn(n, cout, device=dev).to(torch.bfloat16)
+dw = torch.zeros_like(w)
+pairs = km.pairs
+for _ in range(3):
+    ops.conv_wgrad(x, g, pairs, 27, dw, math_mode=1)
 torch.cuda.synchronize()
 print("ok")

@@ -282,8 +282,8 @@ def run_ours(args):
     # A fresh process / fresh box keeps speeding up for a second or two after the first steps (allocator, clocks, host
     # caches): keep warming in windows of 2 * n_batches steps until a window is no more than 3 % faster than the one
     # before it (at most 4 s).  All ranks take the same decision (max over ranks).
-    prev, t_start = None, time.perf_counter()
-    while time.perf_counter() - t_start < 4.0:
+    prev, spent = None, 0.0
+    while spent < 4.0:                                          # `spent` is built from all-reduced times: same on every rank
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(2 * n_batches):
@@ -293,6 +293,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(win, op=dist.ReduceOp.MAX)
         win = float(win.item())
+        spent += win
         n_warm += 2 * n_batches
         if prev is not None and win > 0.97 * prev:
             break

@@ -651,7 +651,11 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   // real kernel maps fill about a quarter of the table.
   const int64_t expect = a->pair_in ? std::max<int64_t>(a->n_pairs / 4, 1) : a->n_pairs;
   int64_t chunk = ceil_div(expect, (int64_t)kNumSMs * 2);
-  chunk = std::max<int64_t>(512, std::min<int64_t>(8192, ceil_div(chunk, kWgPairs) * kWgPairs));
+  // wide outputs: each work item ends with a 128 x Cout reduction into dW, fewer and longer items keep that traffic down
+  // (measured, tools/diag_tc.py: 128->128 at stride 8 23.5 -> 19.5 us, 384->256 58 -> 48 us; narrow layers prefer 512)
+  int64_t chunk_min = a->c_out >= 128 ? 1024 : 512;
+  if (const char* e = getenv("GCD_WG_CHUNK_MIN")) chunk_min = std::max(64, atoi(e));      // tuning aid
+  chunk = std::max<int64_t>(chunk_min, std::min<int64_t>(8192, ceil_div(chunk, kWgPairs) * kWgPairs));
   p.chunk = (int)chunk;
   const int stage_bytes = (2 + p.g_slabs) * kSlabBytes;
   int stages = std::min(kMaxStages, (kSmemBudget - 1024 - 1024) / stage_bytes);

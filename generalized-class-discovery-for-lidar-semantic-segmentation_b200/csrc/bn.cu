@@ -257,7 +257,7 @@ struct ItemWalk {
   __device__ __forceinline__ void next() { g += step_g; r += step_r; if (g >= groups) { g -= groups; ++r; } }
 };
 
-template <typename T, int V, typename F>
+template <typename T, int V, int U, typename F>
 __device__ __forceinline__ void column_reduce2_wide(int64_t n, int c, int rows_per_block, double* __restrict__ sums, F f) {
   __shared__ float red[kVecThreads][2 * V + 1];
   const int groups = c / V;                         // <= 128
@@ -269,14 +269,18 @@ __device__ __forceinline__ void column_reduce2_wide(int64_t n, int c, int rows_p
   if (rl < lanes) {
     const int64_t row_end = min((int64_t)(blockIdx.x + 1) * rows_per_block, n);
     int64_t r = (int64_t)blockIdx.x * rows_per_block + rl;
-    for (; r + lanes < row_end; r += 2 * lanes) {   // two rows in flight
-      float a0[V], b0[V], a1[V], b1[V];
-      f(r, g * V, a0, b0);
-      f(r + lanes, g * V, a1, b1);
+    // U rows in flight per thread (HBM latency x bandwidth needs ~6 MB outstanding over the whole GPU; U = 4 for the
+    // one-operand statistics pass, 2 for the three-operand backward reduction, which is register-bound)
+    for (; r + (U - 1) * (int64_t)lanes < row_end; r += U * lanes) {
+      float a[U][V], b[U][V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) { sa[j] += a0[j] + a1[j]; sb[j] += b0[j] + b1[j]; }
+      for (int u = 0; u < U; ++u) f(r + u * lanes, g * V, a[u], b[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) { sa[j] += a[u][j]; sb[j] += b[u][j]; }
     }
-    if (r < row_end) {
+    for (; r < row_end; r += lanes) {
       float a0[V], b0[V];
       f(r, g * V, a0, b0);
 #pragma unroll
@@ -299,7 +303,7 @@ __device__ __forceinline__ void column_reduce2_wide(int64_t n, int c, int rows_p
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bn_stats_wide_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, int rows_per_block, double* __restrict__ stats) {
   constexpr int V = VecW<T>::V;
-  column_reduce2_wide<T, V>(n, c, rows_per_block, stats, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
+  column_reduce2_wide<T, V, 4>(n, c, rows_per_block, stats, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
     VecW<T>::load(x + r * ld + ch, a);
 #pragma unroll
     for (int j = 0; j < V; ++j) b[j] = a[j] * a[j];
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_reduce_wide_kernel(const T
   __shared__ float s_mean[512], s_is[512];
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) { s_mean[ch] = mean[ch]; s_is[ch] = invstd[ch]; }
   __syncthreads();
-  column_reduce2_wide<T, V>(n, c, rows_per_block, sums, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
+  column_reduce2_wide<T, V, 2>(n, c, rows_per_block, sums, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
     float xv[V], yv[V];
     VecW<T>::load(dy + r * ld_dy + ch, a);
     VecW<T>::load(x + r * ld_x + ch, xv);

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       // that has issued its last stage of tile t goes straight on to its first stage of tile t + 1
       const uint32_t tb = tile_seq & 1;
       mbar_wait(&table_ready[tb], (tile_seq >> 1) & 1);
-      const int32_t* s_nbr = s_nbr0 + tb * (kMaxKV * kTileM);
+      const uint32_t s_nbr_addr = smem_u32(s_nbr0) + tb * (uint32_t)(kMaxKV * kTileM * 4);
       uint32_t mask = s_mask[tb], lo_mask;
       rotate(mask, mask, lo_mask);
       const uint8_t* w_tile = p.w_packed + (int64_t)(work % p.n_tiles_n) * p.n_tile_cols * kRowBytes;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
           if (!(p.ablate & 2))
 #endif
           if (q + 1 < nq || last_active) {
-            const int* nb = s_nbr + k * kTileM + rsub;
+            const uint32_t nb = s_nbr_addr + (uint32_t)(k * kTileM + rsub) * 4u;
             const uint32_t a_stage = a_base + st * kABytes;
             const char* src_q = col_base + q * (kChunkK * 2);
 #pragma unroll
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
               if (((jb >> 3) * G) >> 2 != sub) continue;     // the warp's share of the rows: 32 / G per lane
               int r[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) r[j] = nb[(jb + j) * 4];
+              for (int j = 0; j < 8; ++j) r[j] = lds_s32(nb + (uint32_t)(jb + j) * 16u);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int jj = jb + j;

@@ -70,6 +70,14 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Explicit shared-memory load: pointers derived from the 1024-byte-aligned dynamic smem base lose their address space and
+// compile to generic LD.E otherwise.
+__device__ __forceinline__ int lds_s32(uint32_t smem_addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+  return v;
+}
+
 // ---------------------------------------------------------------- async copies
 // 16-byte cp.async (LDGSTS) with zero fill: src_bytes = 16 copies, 0 writes zeros.
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     const uint32_t d_even = rsub * kRowBytes + ((chunk ^ rsub) << 4);                 // j even: row & 7 == rsub
     const uint32_t d_odd = (rsub + 4) * kRowBytes + ((chunk ^ (rsub + 4)) << 4);      // j odd:  row & 7 == rsub + 4
     const char* col_base = reinterpret_cast<const char*>(p.in + chunk * 8);
-    const int64_t ld_bytes = p.ld_in * 2;
+    const uint32_t ld_bytes = (uint32_t)(p.ld_in * 2);   // row pitch < 4 GB: one 32 x 32 -> 64 bit multiply-add per source address
     const bool last_active = chunk * 8 < last_width;
     const uint32_t a_base = smem_u32(smem + L.a_off);
     const uint32_t b_base = smem_u32(smem + L.b_off);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int jj = jb + j;
-                cp_async_16(a_stage + (jj >> 1) * 1024 + ((jj & 1) ? d_odd : d_even), src_q + (int64_t)max(r[j], 0) * ld_bytes, r[j] >= 0 ? 16u : 0u);
+                cp_async_16(a_stage + (jj >> 1) * 1024 + ((jj & 1) ? d_odd : d_even), src_q + (uint64_t)(uint32_t)max(r[j], 0) * ld_bytes, r[j] >= 0 ? 16u : 0u);
               }
             }
           }
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
     const int chunk16 = lane & 7, rsub = lane >> 3;                          // this lane's pairs of a stage: rsub + 4 j, j = 0..15
     const uint32_t d_even = rsub * kRowBytes + ((chunk16 ^ rsub) << 4);
     const uint32_t d_odd = (rsub + 4) * kRowBytes + ((chunk16 ^ (rsub + 4)) << 4);
-    const int64_t lda = p.ld_in * 2, ldg = p.ld_g * 2;                       // bytes
+    const uint32_t lda = (uint32_t)(p.ld_in * 2), ldg = (uint32_t)(p.ld_g * 2);   // row pitches in bytes (< 4 GB, checked by the host)
     const uint32_t stage0 = smem_u32(smem);
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
     uint32_t g_on = 0;                                                       // bit s: this thread's chunk exists in gradient slab s
@@ -545,8 +545,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
         for (int j = 0; j < 16; ++j) {
           const uint32_t off = (j >> 1) * 1024 + ((j & 1) ? d_odd : d_even);
           const uint32_t n = ri[j] >= 0 ? 16u : 0u;
-          const char* sa = a_col + (int64_t)max(ri[j], 0) * lda;
-          const char* sg = g_col + (int64_t)max(ro[j], 0) * ldg;
+          const char* sa = a_col + (uint64_t)(uint32_t)max(ri[j], 0) * lda;
+          const char* sg = g_col + (uint64_t)(uint32_t)max(ro[j], 0) * ldg;
           if (a_on0) cp_async_16(a_stage + off, sa, n);
           if (a_on1) cp_async_16(a_stage + kSlabBytes + off, sa + 128, n);
 #pragma unroll
@@ -645,6 +645,7 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   p.in = (const __nv_bfloat16*)a->in; p.ld_in = a->ld_in; p.gout = (const __nv_bfloat16*)a->gout; p.ld_g = a->ld_gout;
   p.pair_in = a->pair_in; p.pair_out = a->pair_out; p.pair_off = a->pair_off; p.n_rows_identity = a->n_pairs;
   p.kv = a->kv; p.c_in = a->c_in; p.c_out = a->c_out; p.dw = a->dw;
+  GCD_REQUIRE(a->ld_in > 0 && a->ld_in < (int64_t(1) << 31) && a->ld_gout > 0 && a->ld_gout < (int64_t(1) << 31), "conv_wgrad_tc: row pitch out of range");
   p.m_tiles = (a->c_in + 127) / 128;
   p.g_slabs = (a->c_out + 63) / 64;
   // n_pairs is an upper bound when pair lists are used (the exact count lives on the device);
@@ -705,6 +706,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
     while (tiles_m * p.n_tiles_n * 2 <= kNumSMs && p.n_tile_cols % 32 == 0 && p.n_tile_cols / 2 >= 32) { p.n_tiles_n *= 2; p.n_tile_cols /= 2; }
   }
   p.w_packed = (const uint8_t*)a->w_packed;  // offset mirroring (dgrad of stride-1 maps) is baked into the packed image
+  GCD_REQUIRE(a->ld_in > 0 && a->ld_in < (int64_t(1) << 31), "conv_forward_tc: input row pitch out of range");
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
   int stages = (kSmemBudget - 1024 - 2 * kMaxKV * kTileM * 4 - 512) / stage_bytes;

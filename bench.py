@@ -317,7 +317,8 @@ def run_ours(args):
     # caches): keep warming in windows of 2 * n_batches steps until a window is no more than 3 % faster than the one
     # before it (at most 4 s).  All ranks take the same decision (max over ranks).
     prev, spent = None, 0.0
-    while spent < 4.0:                                          # `spent` is built from all-reduced times: same on every rank
+    fixed_warmup = bool(os.environ.get("GCDLSS_BENCH_FIXED_WARMUP"))   # profiling runs (ncu --launch-skip needs a fixed launch count)
+    while spent < 4.0 and not fixed_warmup:                     # `spent` is built from all-reduced times: same on every rank
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(2 * n_batches):

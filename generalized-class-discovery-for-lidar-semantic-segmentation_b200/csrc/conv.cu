@@ -26,7 +26,11 @@ extern "C" int32_t gcd_conv_forward(const gcd_conv_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (a->math_mode == GCD_MATH_BF16_TCGEN05) {
     if (!conv_forward_tc_supported(a)) { set_error("gcd_conv_forward: shape/dtype not supported by the tcgen05 path (c_in=%d c_out=%d)", a->c_in, a->c_out); return GCD_ERR_UNSUPPORTED; }
-    return conv_forward_tc(a, st);
+    const int32_t rc = conv_forward_tc(a, st);
+    if (rc != GCD_OK || a->stats == nullptr) return rc;
+    // the tcgen05 kernel has no statistics epilogue (measured: it makes the epilogue warps the pacing role on the 1x1 and
+    // 2x2x2 layers); honour the argument with the streaming pass over the result
+    return gcd_bn_stats(a->out, a->ld_out, a->n_out, a->c_out, a->out_dtype, a->stats, stream);
   }
   GCD_REQUIRE(a->w != nullptr, "gcd_conv_forward: fp32 weights required for the SIMT path");
   return conv_forward_simt(a, st);

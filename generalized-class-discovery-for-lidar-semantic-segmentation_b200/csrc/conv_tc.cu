@@ -5,22 +5,22 @@
 //   tile      = 128 output rows x N (<= 256) output channels, fp32 accumulator in TMEM
 //               (two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
 //   iteration = (kernel offset k with at least one hit in the tile) x (64-channel slice of Cin)
-//   warps 0-7 : producers.  Copy the tile's column-major neighbour table into shared memory (the next
-//               tile's entries are prefetched into registers while the current tile streams), then per
-//               iteration gather 128 input rows x 64 bf16 with 16-byte cp.async (zero fill for missing
-//               neighbours) straight into the 128B-swizzled K-major operand image and hand the stage
-//               over with cp.async.mbarrier.arrive (completion-triggered: producers never wait for
-//               their own copies); one thread fetches the matching pre-packed weight slice with a
-//               single bulk copy on the TMA engine (cp.async.bulk -> mbarrier tx count).
-//   warp 12   : one lane issues tcgen05.mma (M=128, N, K=16) per 16 channels and commits to the
-//               stage's "empty" barrier; after the tile's last iteration it commits to "tmem_full".
+//   warps 0-7 : gather producers, each OWNING ring slots (warp w fills the stages of iterations g == w mod stages;
+//               a warp pair per slot when the stages are few and fat).  The owner waits for its slot, posts the
+//               pre-packed weight slice (arrive.expect_tx + one cp.async.bulk on the TMA engine) and gathers the
+//               128 input rows x 64 bf16 itself with 16-byte cp.async (zero fill for missing neighbours) straight into
+//               the 128B-swizzled K-major operand image; cp.async.mbarrier.arrive.noinc publishes the stage when the
+//               copies have landed (the warp never waits for its own copies).
+//   warp 13   : table warp.  Stages the [kv][128] neighbour-table slice of tile t + 1 into the second of two shared
+//               buffers while tile t streams, derives the mask of offsets with a hit and the tile's iteration count
+//               (table_ready / table_free mbarriers; no CTA-wide barrier at tile boundaries).
+//   warp 12   : MMA issuer.  Uniform loop (warp-vote exit) so that stage index, phase and both smem descriptors live in
+//               uniform registers; the elected lane issues tcgen05.mma (M=128, N, K=16) per 16 channels by predicate and
+//               commits to the stage's "empty" barrier; after the tile's last iteration it commits to "tmem_full".
 //   warps 8-11: epilogue.  tcgen05.ld the accumulator (lane == output row), add bias, convert,
 //               store the row; then release the accumulator buffer.
-// Every role is a single instruction stream per warp, so the per-iteration instruction count of each
-// role is what bounds the pipeline (measured: ~1100 cycles/iteration before the loops were stripped of
-// integer divisions, index-load -> copy dependency chains and descriptor rebuilds).  Hence: all
-// addresses that do not depend on the neighbour index are precomputed, indices are loaded once per
-// offset, and the MMA lane only adds constants to prebuilt descriptors.
+// History and measurements (what each of these choices bought, and what did not work): DESIGN.md section 4.1,
+// profiles/README.md, tools/ubench/README.md.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"

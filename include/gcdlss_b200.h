@@ -156,8 +156,10 @@ typedef struct {
   int64_t ld_out;
   int32_t in_dtype;      /* gcd_dtype */
   int32_t out_dtype;     /* gcd_dtype */
-  double* stats;         /* optional [2*c_out] fp64: per-channel sum and sum of squares of the
-                            fp32 result, accumulated atomically (caller zeroes), or NULL */
+  double* stats;         /* optional [2*c_out] fp64: per-channel sum and sum of squares of the result,
+                            accumulated atomically (caller zeroes), or NULL.  SIMT path: from the fp32
+                            accumulator in the epilogue; tcgen05 path: a gcd_bn_stats pass over the
+                            stored tensor issued by the same call */
   int32_t math_mode;     /* gcd_math_mode */
 } gcd_conv_args;
 

@@ -36,6 +36,14 @@ WORKLOADS = {
 METRIC = "MinkUNet fwd+bwd scans/sec"
 
 
+def load_traffic(kernel_class):
+    """DRAM bytes of one captured launch of the kernel class (profiles/traffic.json, from an ncu --set full capture), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel_class)
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -426,8 +434,11 @@ def run_ours(args):
             achieved = info["flops"] / info["time"] / 1e12
             names = {"conv_tc": "conv_fwd_tc_kernel (forward + dgrad launches)", "wgrad_tc": "conv_wgrad_tc_kernel",
                      "conv_simt": "conv_fwd_simt_kernel", "wgrad_simt": "conv_wgrad_simt_kernel"}
+            captured = load_traffic(name)
             roofline = {"kernel": names[name], "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": None,
+                        "frac": achieved / peak, "traffic": captured["bytes"] if captured else None,
+                        "traffic_of": (f"one launch: {captured['launch']}; compulsory {captured['compulsory_bytes']} B; {captured['source']}"
+                                       if captured else None),
                         "peak_source": (peaks["source"] + " bf16_tflops (burst: kernels timed alone, back to back)") if tensor else "nominal fp32 FMA peak",
                         "algorithmic_gflop_per_step": info["flops"] / 1e9, "launches_per_step": info["launches"],
                         "avg_launch_us": info["time"] / info["launches"] * 1e6, "kernel_ms_per_step": info["time"] * 1e3,

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/gcdlss_b200.h"
+#include "keys.cuh"
 
 namespace gcd {
 
@@ -31,35 +32,6 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 constexpr int kNumSMs = 148;  // B200
-
-// ---- 64-bit coordinate keys: 10 bits batch | 3 x 18 bits (coord + 2^17)
-constexpr int kCoordBits = 18;
-constexpr int kCoordBias = 1 << (kCoordBits - 1);
-constexpr int kBatchBits = 10;
-constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
-
-__device__ __forceinline__ bool key_in_range(int b, int x, int y, int z) {
-  const unsigned lim = 1u << kCoordBits;
-  return (unsigned)b < (1u << kBatchBits) - 1u &&  // batch 1023 reserved: keeps every key != kEmptyKey
-         (unsigned)(x + kCoordBias) < lim &&
-         (unsigned)(y + kCoordBias) < lim && (unsigned)(z + kCoordBias) < lim;
-}
-__device__ __forceinline__ uint64_t pack_key(int b, int x, int y, int z) {
-  return ((uint64_t)(unsigned)b << (3 * kCoordBits)) | ((uint64_t)(unsigned)(x + kCoordBias) << (2 * kCoordBits)) |
-         ((uint64_t)(unsigned)(y + kCoordBias) << kCoordBits) | (uint64_t)(unsigned)(z + kCoordBias);
-}
-__device__ __forceinline__ void unpack_key(uint64_t k, int& b, int& x, int& y, int& z) {
-  const uint64_t m = (1ull << kCoordBits) - 1;
-  z = (int)(k & m) - kCoordBias;
-  y = (int)((k >> kCoordBits) & m) - kCoordBias;
-  x = (int)((k >> (2 * kCoordBits)) & m) - kCoordBias;
-  b = (int)(k >> (3 * kCoordBits));
-}
-// murmur3 finaliser
-__device__ __forceinline__ uint64_t hash_key(uint64_t k) {
-  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-  return k;
-}
 
 // Open-addressing table, linear probing.  Slots are grouped in 32-byte sectors of four keys; a
 // probe sequence visits whole sectors so the four keys a DRAM/L2 sector delivers are all used.

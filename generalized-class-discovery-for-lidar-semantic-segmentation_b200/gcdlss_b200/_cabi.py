@@ -121,6 +121,9 @@ PROTOTYPES = {
     "gcd_kmap_subm": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "gcd_kmap_down2": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "gcd_kmap_up2": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "gcd_runtable_slot_bytes": (_sz, []),
+    "gcd_runtable_build": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp]),
+    "gcd_kmap_subm_runs": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
     "gcd_pairs_workspace_bytes": (_sz, [_i64, _i32]),
     "gcd_pairs_from_table": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gcd_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),

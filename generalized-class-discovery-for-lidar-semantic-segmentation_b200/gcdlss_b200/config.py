@@ -21,3 +21,23 @@ def set_math_mode(mode: str) -> None:
 
 def get_math_mode() -> str:
     return _state["mode"]
+
+
+# Kernel-map search of the stride-1 convolutions.  "points": one hash slot per voxel (gcd_hash_build + gcd_kmap_subm).
+# "runs": one 32-byte slot per run of four x-adjacent cells (gcd_runtable_build + gcd_kmap_subm_runs, csrc/runtable.cuh):
+# the same maps from 2.4-2.8x fewer scattered loads.  The run table's logic is held to the oracle on the CPU by
+# tests/test_emulated_kernels.py; it becomes the default once tests/test_gpu_zz_runtable.py has passed on a B200.
+_KMAP = ("points", "runs")
+_state["kmap"] = os.environ.get("GCDLSS_KMAP", "points")
+if _state["kmap"] not in _KMAP:
+    raise ValueError(f"GCDLSS_KMAP must be one of {_KMAP}")
+
+
+def set_kmap_search(kind: str) -> None:
+    if kind not in _KMAP:
+        raise ValueError(f"kernel-map search must be one of {_KMAP}")
+    _state["kmap"] = kind
+
+
+def get_kmap_search() -> str:
+    return _state["kmap"]

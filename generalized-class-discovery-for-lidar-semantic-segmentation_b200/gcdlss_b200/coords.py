@@ -11,14 +11,15 @@ import weakref
 
 import torch
 
-from . import ops
+from . import config, ops
 
 
 class CoordMap:
-    __slots__ = ("coords", "n", "table", "tensor_stride", "parent", "code")
+    __slots__ = ("coords", "n", "table", "runs", "tensor_stride", "parent", "code")
 
-    def __init__(self, coords, table, tensor_stride):
+    def __init__(self, coords, table, tensor_stride, runs=None):
         self.coords, self.n, self.table, self.tensor_stride = coords, coords.shape[0], table, tensor_stride
+        self.runs = runs     # run table (config "runs" kernel-map search); `table` is the point-wise one (may be None then)
         self.parent = None   # [n] row of the 2x coarser map (filled when that map is created)
         self.code = None     # [n] child offset index dx + 2dy + 4dz
 
@@ -69,7 +70,11 @@ class CoordinateManager:
         ops.new_batch()
         self.device = coords.device
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.maps = {1: CoordMap(coords, ops.hash_build(coords, self.status), 1)}
+        self.runs = config.get_kmap_search() == "runs"
+        if self.runs:    # the run-table build reports duplicates / range errors like gcd_hash_build does
+            self.maps = {1: CoordMap(coords, None, 1, ops.runtable_build(coords, 1, self.status))}
+        else:
+            self.maps = {1: CoordMap(coords, ops.hash_build(coords, self.status), 1)}
         self._kmaps = {}
 
     # -- coordinate maps -------------------------------------------------------------------
@@ -107,7 +112,11 @@ class CoordinateManager:
         """Every device tensor this manager owns (for cross-stream hand-over)."""
         out = [self.status]
         for m in self.maps.values():
-            out += [m.coords, m.table.keys, m.table.vals]
+            out.append(m.coords)
+            if m.table is not None:
+                out += [m.table.keys, m.table.vals]
+            if m.runs is not None:
+                out.append(m.runs.slots)
             out += [t for t in (m.parent, m.code) if t is not None]
         for km in self._kmaps.values():
             if km.nbr is not None:
@@ -127,7 +136,12 @@ class CoordinateManager:
             km = KernelMap(None, m.n, m.n, 1, self, None, False)
         elif stride == 1 and kernel_size in (3, 5) and not transposed:
             m = self.get_map(ts_in)
-            nbr = ops.kmap_subm(m.coords, m.table, kernel_size, ts_in)
+            if self.runs:
+                if m.runs is None:       # coarse maps: built on first use from the map's unique coordinates
+                    m.runs = ops.runtable_build(m.coords, ts_in, self.status)
+                nbr = ops.kmap_subm_runs(m.coords, m.runs, kernel_size, ts_in)
+            else:
+                nbr = ops.kmap_subm(m.coords, m.table, kernel_size, ts_in)
             # stride-1 symmetric kernel: the transposed map is the same table with mirrored offsets
             km = KernelMap(nbr, m.n, m.n, kernel_size ** 3, self, "self", True)
         elif stride == 2 and kernel_size == 2 and not transposed:

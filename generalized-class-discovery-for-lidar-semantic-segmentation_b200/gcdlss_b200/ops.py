@@ -226,6 +226,34 @@ def kmap_subm(coords: torch.Tensor, table: HashTable, kernel_size: int, ts: int)
     return nbr
 
 
+class RunTable:
+    """Device memory of one run table: ``cap`` 32-byte slots (csrc/runtable.cuh), int64 storage so the base is 32-byte aligned."""
+
+    def __init__(self, n: int, device):
+        self.cap = int(lib().gcd_hash_capacity(n))
+        words = int(lib().gcd_runtable_slot_bytes()) // 8
+        self.slots = torch.empty((self.cap, words), dtype=torch.int64, device=device)
+
+
+def runtable_build(coords: torch.Tensor, ts: int, status: torch.Tensor) -> RunTable:
+    """Run table of the unique int32 [n, 4] coordinates of one map at tensor stride ``ts``."""
+    n = coords.shape[0]
+    table = RunTable(n, coords.device)
+    call("gcd_runtable_build", _ptr(coords), n, ts, _ptr(table.slots), table.cap, _ptr(status), _stream())
+    _count(2)
+    return table
+
+
+def kmap_subm_runs(coords: torch.Tensor, table: RunTable, kernel_size: int, ts: int) -> torch.Tensor:
+    """Same result as :func:`kmap_subm`, searched in a run table."""
+    n = coords.shape[0]
+    kv = kernel_size ** 3
+    nbr = torch.empty((kv, n), dtype=torch.int32, device=coords.device)
+    call("gcd_kmap_subm_runs", _ptr(coords), n, _ptr(table.slots), table.cap, kernel_size, ts, _ptr(nbr), _stream())
+    _count()
+    return nbr
+
+
 def kmap_down2(parent, code, n_coarse: int) -> torch.Tensor:
     nbr = torch.empty((8, n_coarse), dtype=torch.int32, device=parent.device)
     call("gcd_kmap_down2", _ptr(parent), _ptr(code), parent.shape[0], n_coarse, _ptr(nbr), _stream())

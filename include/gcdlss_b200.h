@@ -125,6 +125,20 @@ int32_t gcd_kmap_down2(const int32_t* parent, const int32_t* code, int64_t n_fin
                        int32_t* nbr, void* stream);
 int32_t gcd_kmap_up2(const int32_t* parent, const int32_t* code, int64_t n_fine, int32_t* nbr, void* stream);
 
+/* Run table (opt-in, GCDLSS_KMAP=runs): the same stride-1 kernel maps from a hash whose 32-byte slots hold runs of
+ * four x-adjacent cells of one (b, y, z) row, so the K neighbours of a row cost one or two sector loads instead of K
+ * key loads + K value loads (csrc/runtable.cuh).  Replaces, for this purpose, the table ME builds per coordinate map
+ * (ME.SparseTensor(coordinates=...), modules/exp.py:259) and the per-offset search behind every stride-1
+ * MinkowskiConvolution (models/minkunet.py:62-128).
+ * slots: caller-owned, 32-byte aligned, cap * gcd_runtable_slot_bytes() bytes, cap = gcd_hash_capacity(n).
+ * gcd_runtable_build: inserts n unique rows whose x is a multiple of ts (status: key range / duplicate / full).
+ * gcd_kmap_subm_runs: nbr [K^3][n] column-major, bit-identical to gcd_kmap_subm. */
+size_t gcd_runtable_slot_bytes(void);
+int32_t gcd_runtable_build(const int32_t* coords, int64_t n, int32_t ts, void* slots, int64_t cap,
+                           int32_t* status, void* stream);
+int32_t gcd_kmap_subm_runs(const int32_t* coords, int64_t n, const void* slots, int64_t cap,
+                           int32_t kernel_size, int32_t ts, int32_t* nbr, void* stream);
+
 size_t gcd_pairs_workspace_bytes(int64_t n_out, int32_t kv);
 /* Per-offset pair lists of a table: pairs of offset k are [pair_off[k], pair_off[k+1]), sorted by
  * output row.  pair_in / pair_out hold up to n_out*kv entries; pair_off is int32 [kv+1] (device). */

@@ -54,6 +54,14 @@ report("coords_stride2 (insert+scan+emit)", t, m * 16 + m * 8 + coarse.shape[0] 
 for K in (3, 5):
     t = timeit(lambda: ops.kmap_subm(bc, tb, K, 1), reps=10, flush=flush)
     report(f"kmap_subm_kernel<{K}>", t, m * 16 + K**3 * m * 8 + K**3 * m * 4)
+# the same tables searched in a run table (csrc/runtable.cuh, GCDLSS_KMAP=runs); same algorithmic bytes
+t = timeit(lambda: ops.runtable_build(bc, 1, status), flush=flush)
+rt = ops.runtable_build(bc, 1, status)
+report("runtable_build (clear + insert)", t, m * 16 + rt.cap * 32)
+for K in (3, 5):
+    t = timeit(lambda: ops.kmap_subm_runs(bc, rt, K, 1), reps=10, flush=flush)
+    report(f"kmap_runs_kernel<{K}>", t, m * 16 + K**3 * m * 8 + K**3 * m * 4)
+    assert torch.equal(ops.kmap_subm_runs(bc, rt, K, 1), ops.kmap_subm(bc, tb, K, 1))
 nbr = ops.kmap_subm(bc, tb, 3, 1)
 t = timeit(lambda: ops.pairs_from_table(nbr), reps=10, flush=flush)
 p = int(ops.pairs_from_table(nbr)[2][-1])

@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of round 2: everything written after round 1's GPU budget ran out, each step under its own timeout.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Results land in gpurun_out/r2_*.  Opt-in variants under test:
+#   GCDLSS_KMAP=runs    kernel-map search over x-runs (csrc/runtable.cuh)          -> default if parity + faster
+#   GCD_TC_COMPACT=1    forward/dgrad conv: compacted row copies (csrc/conv_tc.cu) -> default if parity + faster
+mkdir -p gpurun_out
+run() { name=$1; shift; timeout "$1" "${@:2}" > gpurun_out/r2_$name.log 2>&1; echo "$name rc=$?"; tail -3 gpurun_out/r2_$name.log; }
+run tests          900 python -m pytest tests -m gpu -q --timeout 300 --timeout-method thread
+run smoke          300 python -c "import __graft_entry__ as g; g.smoke()"
+run maps           300 python tools/bench_maps.py
+run bench_default  600 python bench.py --steps 20 --warmup 5
+GCDLSS_KMAP=runs   run tests_runs    600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
+GCDLSS_KMAP=runs   run bench_runs    600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+GCD_TC_COMPACT=1   run tests_compact 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
+GCD_TC_COMPACT=1   run layers_compact 300 python tools/diag_tc.py
+run layers_default 300 python tools/diag_tc.py
+GCD_TC_COMPACT=1   run bench_compact 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+# fresh launch list of the default path (fixed warm-up so --launch-skip lands inside the timed region)
+GCDLSS_BENCH_FIXED_WARMUP=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 4000 -c 1800 --csv \
+  --log-file gpurun_out/r2_launches.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2_ncu.log 2>&1; echo "ncu rc=$?"

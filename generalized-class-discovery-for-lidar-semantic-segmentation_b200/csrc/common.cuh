@@ -75,5 +75,9 @@ size_t scan_workspace_bytes(int64_t n);
 // out[i] = sum_{j<i} in[j]; total (device int32, may be null) = sum of all.  in may alias out.
 int32_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* total, void* workspace,
                            size_t workspace_bytes, cudaStream_t stream);
+// pair lists straight from a neighbour table (scan.cu): two reads of the table, no flag / position arrays.
+// total_pairs: device int32 scratch; workspace >= scan_workspace_bytes(n_out * kv).
+int32_t pairs_from_table_fused(const int32_t* nbr, int64_t n_out, int kv, int32_t* pair_in, int32_t* pair_out, int32_t* pair_off,
+                               int32_t* total_pairs, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace gcd

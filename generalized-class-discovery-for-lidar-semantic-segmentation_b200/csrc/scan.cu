@@ -81,7 +81,67 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int32_t* __restr
   for (int i = 0; i < kScanItems; ++i)
     if (base + i < n) out[base + i] += add;
 }
+
+// ---- fused pair-list build (opt-in, GCD_PAIRS_FUSED=1): the flattened table [kv * n_out] is read twice and nothing but
+// the pair lists is written (the three-pass version writes and re-reads a flag array and a position array of the table's
+// size: 8 passes over 4 * kv * n_out bytes instead of 2).  Same tiling and the same block scan as scan_tiles_kernel, so the
+// positions -- and therefore the lists -- are identical.
+__global__ void __launch_bounds__(kScanThreads) pairs_count_kernel(const int32_t* __restrict__ nbr, int64_t total_entries,
+                                                                    int32_t* __restrict__ tile_sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) sum += (base + i < total_entries && nbr[base + i] >= 0) ? 1 : 0;
+  int total;
+  block_exclusive_scan(sum, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// tile_sums holds the exclusive scan of the tile counts; total_pairs the grand total.
+__global__ void __launch_bounds__(kScanThreads) pairs_emit_fused_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int kv,
+                                                                         const int32_t* __restrict__ tile_sums,
+                                                                         const int32_t* __restrict__ total_pairs,
+                                                                         int32_t* __restrict__ pair_in, int32_t* __restrict__ pair_out,
+                                                                         int32_t* __restrict__ pair_off) {
+  const int64_t total_entries = n_out * kv;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < total_entries) ? nbr[base + i] : -1;
+    sum += v[i] >= 0 ? 1 : 0;
+  }
+  int total;
+  int pos = block_exclusive_scan(sum, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const int64_t t = base + i;
+    if (t < total_entries) {
+      const int64_t k = t / n_out, o = t - k * n_out;
+      if (o == 0) pair_off[k] = pos;                       // first entry of offset k: where its list starts
+      if (v[i] >= 0) { pair_in[pos] = v[i]; pair_out[pos] = (int32_t)o; ++pos; }
+      if (t == total_entries - 1) pair_off[kv] = *total_pairs;
+    }
+  }
+}
 }  // namespace
+
+int32_t pairs_from_table_fused(const int32_t* nbr, int64_t n_out, int kv, int32_t* pair_in, int32_t* pair_out, int32_t* pair_off,
+                               int32_t* total_pairs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int64_t total_entries = n_out * kv;
+  if (workspace_bytes < scan_workspace_bytes(total_entries)) {
+    set_error("pairs_from_table_fused: workspace too small");
+    return GCD_ERR_WORKSPACE;
+  }
+  int32_t* sums = static_cast<int32_t*>(workspace);
+  const int64_t n_tiles = ceil_div(total_entries, kScanTile);
+  pairs_count_kernel<<<(unsigned)n_tiles, kScanThreads, 0, stream>>>(nbr, total_entries, sums);
+  scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(sums, n_tiles, total_pairs);
+  pairs_emit_fused_kernel<<<(unsigned)n_tiles, kScanThreads, 0, stream>>>(nbr, n_out, kv, sums, total_pairs, pair_in, pair_out, pair_off);
+  GCD_LAUNCH_CHECK("gcd_pairs_from_table(fused)");
+  return GCD_OK;
+}
 
 size_t scan_workspace_bytes(int64_t n) { return align_up((size_t)(ceil_div(n > 0 ? n : 1, kScanTile)) * sizeof(int32_t), 256); }
 

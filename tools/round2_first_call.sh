@@ -3,6 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 # Results land in gpurun_out/r2_*.  Opt-in variants under test:
 #   GCDLSS_KMAP=runs    kernel-map search over x-runs (csrc/runtable.cuh)          -> default if parity + faster
+#   GCD_PAIRS_FUSED=1   pair lists straight from the table, 2 passes instead of 8 (csrc/scan.cu) -> default if parity + faster
 #   GCD_TC_COMPACT=1    forward/dgrad conv: compacted row copies (csrc/conv_tc.cu) -> default if parity + faster
 mkdir -p gpurun_out
 run() { name=$1; shift; timeout "$1" "${@:2}" > gpurun_out/r2_$name.log 2>&1; echo "$name rc=$?"; tail -3 gpurun_out/r2_$name.log; }
@@ -12,6 +13,8 @@ run maps           300 python tools/bench_maps.py
 run bench_default  600 python bench.py --steps 20 --warmup 5
 GCDLSS_KMAP=runs   run tests_runs    600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
 GCDLSS_KMAP=runs   run bench_runs    600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+GCD_PAIRS_FUSED=1  run tests_pairs   600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_conv.py -m gpu -q --timeout 300 --timeout-method thread
+GCD_PAIRS_FUSED=1  run maps_pairs    300 python tools/bench_maps.py
 GCD_TC_COMPACT=1   run tests_compact 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_TC_COMPACT=1   run layers_compact 300 python tools/diag_tc.py
 run layers_default 300 python tools/diag_tc.py

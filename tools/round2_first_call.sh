@@ -19,6 +19,8 @@ GCD_TC_COMPACT=1   run tests_compact 600 python -m pytest tests/test_gpu_conv.py
 GCD_TC_COMPACT=1   run layers_compact 300 python tools/diag_tc.py
 run layers_default 300 python tools/diag_tc.py
 GCD_TC_COMPACT=1   run bench_compact 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+( cd tools/ubench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../generalized-class-discovery-for-lidar-semantic-segmentation_b200/csrc -o smem_port smem_port.cu ) > /dev/null 2>&1
+run smem_port      120 tools/ubench/smem_port
 # fresh launch list of the default path (fixed warm-up so --launch-skip lands inside the timed region)
 GCDLSS_BENCH_FIXED_WARMUP=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 4000 -c 1800 --csv \
   --log-file gpurun_out/r2_launches.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2_ncu.log 2>&1; echo "ncu rc=$?"

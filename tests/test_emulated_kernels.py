@@ -4,6 +4,7 @@ logic of the CUDA path is checked here and only its hardware-specific parts (the
 left to tests/test_gpu_zz_runtable.py."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 
 import numpy as np
@@ -19,6 +20,8 @@ EMU = os.path.join(ROOT, "tests", "emu")
 
 @pytest.fixture(scope="session")
 def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
     out = str(tmp_path_factory.mktemp("emu") / "librt_emu.so")
     subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-psabi", "-shared", "-fPIC", "-I", CSRC, "-o", out, os.path.join(EMU, "runtable_emu.cpp")],
                    check=True, capture_output=True)

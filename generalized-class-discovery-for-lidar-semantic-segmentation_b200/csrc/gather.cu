@@ -1,7 +1,9 @@
 // gather.cu — voxel<->point movement: devoxelisation gather, CSR grouping of points by voxel,
 // and segmented sum / mean / max (the gather's backward and the point->voxel encoder reduce).
 #include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
+#include "gather_rows.cuh"
 
 namespace gcd {
 size_t radix_sort_workspace_bytes(int64_t n);
@@ -22,6 +24,13 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const float* __restric
   } else {
     for (int j = lane; j < c; j += 32) out[row * ld_out + j] = __ldg(&in[src * ld_in + j]);
   }
+}
+
+// Vectorised case: float4 elements dealt flat to threads, four independent chains per thread (gather_rows.cuh).
+__global__ void __launch_bounds__(kGatherThreads) rows_gather_flat_kernel(const float4* __restrict__ in, int64_t ld_in4,
+                                                                          const int64_t* __restrict__ idx, int64_t n_out, int c4,
+                                                                          float4* __restrict__ out, int64_t ld_out4) {
+  rows_gather_flat_thread<float4>(blockIdx.x, threadIdx.x, in, ld_in4, idx, n_out, c4, out, ld_out4);
 }
 
 __global__ void __launch_bounds__(256) csr_keys_kernel(const int64_t* __restrict__ idx, int64_t n, uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
@@ -64,6 +73,11 @@ extern "C" int32_t gcd_rows_gather(const float* in, int64_t ld_in, const int64_t
   if (n_out == 0) return GCD_OK;
   const int vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  static const bool flat = getenv("GCD_GATHER_FLAT") && atoi(getenv("GCD_GATHER_FLAT")) != 0;   // opt-in until run on a B200
+  if (vec && flat)
+    rows_gather_flat_kernel<<<(unsigned)ceil_div(n_out * (c / 4), kGatherThreads * kGatherUnroll), kGatherThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(in), ld_in / 4, idx, n_out, c / 4, reinterpret_cast<float4*>(out), ld_out / 4);
+  else
   rows_gather_kernel<<<(unsigned)ceil_div(n_out * 32, 256), 256, 0, as_stream(stream)>>>(in, ld_in, idx, n_out, c, out, ld_out, vec);
   GCD_LAUNCH_CHECK("gcd_rows_gather");
   return GCD_OK;

@@ -31,6 +31,16 @@ def emu(tmp_path_factory):
     return lib
 
 
+@pytest.fixture(scope="session")
+def emu_gather(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("emu") / "libgather_emu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, "-o", out, os.path.join(EMU, "gather_emu.cpp")],
+                   check=True, capture_output=True)
+    return C.CDLL(out)
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -164,3 +174,16 @@ def test_empty_and_single(emu):
     slots, cap, status = build(emu, one, 1)
     nbr = kmap(emu, one, slots, cap, 3, 1)
     assert status == 0 and nbr[13, 0] == 0 and (np.delete(nbr[:, 0], 13) == -1).all()
+
+
+@pytest.mark.parametrize("n_in,n_out,c,pad_in,pad_out", [(50, 1, 4, 0, 0), (300, 1000, 96, 0, 0), (300, 1037, 96, 4, 8), (17, 4099, 100, 0, 12),
+                                                           (9, 513, 256, 0, 0), (64, 2048, 16, 0, 0), (5, 0, 96, 0, 0)])
+def test_flat_gather_is_a_row_copy(emu_gather, n_in, n_out, c, pad_in, pad_out):
+    # devoxelise gather (csrc/gather_rows.cuh): every element of out[i, :c] == in[idx[i], :c], padding columns untouched
+    rng = np.random.default_rng(n_out + c)
+    src = rng.normal(size=(n_in, c + pad_in)).astype(np.float32)
+    idx = rng.integers(0, n_in, n_out).astype(np.int64)
+    out = np.full((max(n_out, 1), c + pad_out), -3.0, np.float32)
+    emu_gather.emu_rows_gather_flat(_ptr(src), C.c_int64(c + pad_in), _ptr(idx), C.c_int64(n_out), C.c_int32(c), _ptr(out), C.c_int64(c + pad_out))
+    np.testing.assert_array_equal(out[:n_out, :c], src[idx][:, :c])
+    assert (out[:n_out, c:] == -3.0).all() and (out[n_out:] == -3.0).all()

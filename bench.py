@@ -405,6 +405,8 @@ def run_ours(args):
                 pair_count[km.nbr.data_ptr()] = n_pairs
                 if km._pairs is not None:
                     pair_count[km._pairs[0].data_ptr()] = n_pairs
+                if getattr(km, "_sorted", None) is not None:          # tile-sorted copy (GCDLSS_TILE_SORT=1): same pairs
+                    pair_count[km._sorted[0].data_ptr()] = n_pairs
         classes = {}
         for kind_k, ptr, n_out, kv, c_in, c_out, fn in ops.kernel_timer.captured:
             pairs = n_out if ptr == 0 else pair_count.get(ptr, n_out)

@@ -63,6 +63,7 @@ int32_t unit_conv(const gcd_convbn* u, const void* in, int64_t ld_in, void* out,
   a.mirror = 0; a.bias = nullptr; a.out = out; a.ld_out = u->c_out;
   a.in_dtype = dtype; a.out_dtype = dtype; a.stats = nullptr;
   a.math_mode = u->w_packed_fwd ? GCD_MATH_BF16_TCGEN05 : GCD_MATH_FP32_SIMT;
+  a.out_rows = u->out_rows;
   return gcd_conv_forward(&a, stream);
 }
 
@@ -75,6 +76,7 @@ int32_t unit_dgrad(const gcd_convbn* u, const void* dy, void* dx, int32_t dtype,
   a.mirror = u->back_mirror; a.bias = nullptr; a.out = dx; a.ld_out = u->c_in;
   a.in_dtype = dtype; a.out_dtype = dtype; a.stats = nullptr;
   a.math_mode = u->w_packed_bwd ? GCD_MATH_BF16_TCGEN05 : GCD_MATH_FP32_SIMT;
+  a.out_rows = u->back_out_rows;
   return gcd_conv_forward(&a, stream);
 }
 

@@ -33,6 +33,7 @@ extern "C" int32_t gcd_conv_forward(const gcd_conv_args* a, void* stream) {
     return gcd_bn_stats(a->out, a->ld_out, a->n_out, a->c_out, a->out_dtype, a->stats, stream);
   }
   GCD_REQUIRE(a->w != nullptr, "gcd_conv_forward: fp32 weights required for the SIMT path");
+  GCD_REQUIRE(a->out_rows == nullptr, "gcd_conv_forward: tile-sorted tables (out_rows) are a tcgen05-path feature");
   return conv_forward_simt(a, st);
 }
 

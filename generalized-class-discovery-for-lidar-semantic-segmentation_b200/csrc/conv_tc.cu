@@ -58,6 +58,7 @@ struct FwdParams {
   void* out; int64_t ld_out; int out_is_bf16;
   int stages;
   int group;                       // producer warps that share one stage (1, 2, 4, 8)
+  const int32_t* out_rows;         // kPerm kernels: output row of table column i (tile-sorted table, tilesort.cu)
 #ifdef GCD_TC_PROFILE
   long long* dbg;
   int ablate;                      // profile build only: 1 = no MMA issue, 2 = no gather copies, 4 = weight copies of 16 B
@@ -83,7 +84,8 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
 // With kNQ known the slice loop is unrolled and every copy uses an immediate offset from a per-offset base
 // pointer, which is what keeps the producer loop at a few dozen instructions per stage.
 // kCompact (opt-in, GCD_TC_COMPACT=1, not yet measured on hardware): the owner copies only the rows that need touching.
-template <int kNQ, bool kCompact = false>
+// kPerm (opt-in, tile-sorted tables): table column i is output row p.out_rows[i]; only the epilogue's store address changes.
+template <int kNQ, bool kCompact = false, bool kPerm = false>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is at least 16-byte aligned; the swizzle pattern needs 1024.
@@ -378,6 +380,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       mbar_wait_warp(&tmem_full[buf], (tile_seq >> 1) & 1, 128);
       tc_fence_after();
       const int64_t row = tm * kTileM + ew * 32 + lane;
+      int64_t orow = row;                        // where this accumulator lane's row goes
+      if constexpr (kPerm) { if (row < p.n_out) orow = p.out_rows[row]; }
       const int col0 = tn * p.n_tile_cols;
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)(ew * 32) << 16);
       for (int c = 0; c < p.n_tile_cols; c += 16) {
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[col0 + c + j] : 0.f);
           if (p.out_is_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + col0 + c;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ld_out + col0 + c;
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
             *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
           } else {
-            float* o = reinterpret_cast<float*>(p.out) + row * p.ld_out + col0 + c;
+            float* o = reinterpret_cast<float*>(p.out) + orow * p.ld_out + col0 + c;
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
@@ -728,6 +732,19 @@ bool conv_forward_tc_supported(const gcd_conv_args* a) {
          (a->out_dtype == GCD_BF16 ? (a->ld_out % 8 == 0) : (a->ld_out % 4 == 0)) && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;
 }
 
+using FwdKernel = void (*)(const FwdParams);
+template <bool kCompact, bool kPerm>
+FwdKernel pick_fwd_kernel(int nq) {
+  switch (nq) {
+    case 1: return conv_fwd_tc_kernel<1, kCompact, kPerm>;
+    case 2: return conv_fwd_tc_kernel<2, kCompact, kPerm>;
+    case 3: return conv_fwd_tc_kernel<3, kCompact, kPerm>;
+    case 4: return conv_fwd_tc_kernel<4, kCompact, kPerm>;
+    case 6: return conv_fwd_tc_kernel<6, kCompact, kPerm>;
+    default: return conv_fwd_tc_kernel<0, kCompact, kPerm>;
+  }
+}
+
 int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   FwdParams p;
   p.in = (const __nv_bfloat16*)a->in; p.ld_in = a->ld_in; p.nbr = a->nbr; p.kv = a->kv; p.n_out = a->n_out;
@@ -745,6 +762,8 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.w_packed = (const uint8_t*)a->w_packed;  // offset mirroring (dgrad of stride-1 maps) is baked into the packed image
   GCD_REQUIRE(a->ld_in > 0 && a->ld_in < (int64_t(1) << 31), "conv_forward_tc: input row pitch out of range");
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
+  p.out_rows = a->out_rows;
+  GCD_REQUIRE(a->out_rows == nullptr || a->nbr != nullptr, "conv_forward_tc: out_rows needs a neighbour table");
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
   int stages = (kSmemBudget - 1024 - 2 * kMaxKV * kTileM * 4 - 512) / stage_bytes;
   stages = std::min(stages, kMaxStages);
@@ -759,29 +778,23 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
 #endif
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;
-  using Kernel = void (*)(const FwdParams);
   // Compacted row copies (opt-in until measured on a B200): needs a fixed slot per owner group (owner groups == stages).
   static const bool want_compact = getenv("GCD_TC_COMPACT") && atoi(getenv("GCD_TC_COMPACT")) != 0;
   const bool compact = want_compact && p.group <= 4 && kProducerWarps / p.group >= stages;
-  Kernel kernel;
-  switch ((a->c_in + kChunkK - 1) / kChunkK) {
-    case 1: kernel = compact ? conv_fwd_tc_kernel<1, true> : conv_fwd_tc_kernel<1>; break;
-    case 2: kernel = compact ? conv_fwd_tc_kernel<2, true> : conv_fwd_tc_kernel<2>; break;
-    case 3: kernel = compact ? conv_fwd_tc_kernel<3, true> : conv_fwd_tc_kernel<3>; break;
-    case 4: kernel = compact ? conv_fwd_tc_kernel<4, true> : conv_fwd_tc_kernel<4>; break;
-    case 6: kernel = compact ? conv_fwd_tc_kernel<6, true> : conv_fwd_tc_kernel<6>; break;
-    default: kernel = compact ? conv_fwd_tc_kernel<0, true> : conv_fwd_tc_kernel<0>; break;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (Kernel k : {(Kernel)conv_fwd_tc_kernel<0>, (Kernel)conv_fwd_tc_kernel<1>, (Kernel)conv_fwd_tc_kernel<2>, (Kernel)conv_fwd_tc_kernel<3>,
-                     (Kernel)conv_fwd_tc_kernel<4>, (Kernel)conv_fwd_tc_kernel<6>,
-                     (Kernel)conv_fwd_tc_kernel<0, true>, (Kernel)conv_fwd_tc_kernel<1, true>, (Kernel)conv_fwd_tc_kernel<2, true>,
-                     (Kernel)conv_fwd_tc_kernel<3, true>, (Kernel)conv_fwd_tc_kernel<4, true>, (Kernel)conv_fwd_tc_kernel<6, true>}) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+  const int nq_sel = (a->c_in + kChunkK - 1) / kChunkK;
+  const FwdKernel kernel = compact ? (p.out_rows ? pick_fwd_kernel<true, true>(nq_sel) : pick_fwd_kernel<true, false>(nq_sel))
+                                   : (p.out_rows ? pick_fwd_kernel<false, true>(nq_sel) : pick_fwd_kernel<false, false>(nq_sel));
+  {
+    // opt-in to the large dynamic shared memory once per kernel instantiation (benign race: the call is idempotent)
+    static FwdKernel done[32];
+    static int n_done = 0;
+    bool seen = false;
+    for (int i = 0; i < n_done; ++i) seen = seen || done[i] == kernel;
+    if (!seen) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_fwd_tc_kernel)");
+      if (n_done < 32) done[n_done++] = kernel;
     }
-    attr_set = true;
   }
   if (a->c_in > 8 * kChunkK) { set_error("conv_forward_tc: more than 512 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;

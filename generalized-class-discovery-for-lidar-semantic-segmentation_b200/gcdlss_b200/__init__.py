@@ -4,7 +4,7 @@ Host-side mirror of the MinkowskiEngine surface the GCDLSS reference calls; all 
 hand-written CUDA kernels behind the C ABI of ``libgcdlss_sm100a.so`` (include/gcdlss_b200.h).
 """
 from . import _cabi
-from .config import get_kmap_search, get_math_mode, set_kmap_search, set_math_mode
+from .config import get_kmap_search, get_math_mode, get_tile_sort, set_kmap_search, set_math_mode, set_tile_sort
 from .coords import CoordinateManager, KernelMap
 from .functional import devoxelize, voxelize_reduce
 from .nn import (BasicBlock, Bottleneck, MinkowskiBatchNorm, MinkowskiConvolution, MinkowskiConvolutionTranspose, MinkowskiDropout,

@@ -57,6 +57,7 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64),
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
         ("stats", C.c_void_p), ("math_mode", C.c_int32),
+        ("out_rows", C.c_void_p),
     ]
 
 
@@ -84,6 +85,7 @@ class ConvBnUnit(C.Structure):
         ("eps", C.c_float), ("momentum", C.c_float),
         ("stats", C.c_void_p), ("sums", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
         ("dw", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("out_rows", C.c_void_p), ("back_out_rows", C.c_void_p),
     ]
 
 
@@ -124,6 +126,8 @@ PROTOTYPES = {
     "gcd_runtable_slot_bytes": (_sz, []),
     "gcd_runtable_build": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     "gcd_kmap_subm_runs": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "gcd_tile_sort_workspace_bytes": (_sz, [_i64]),
+    "gcd_kmap_tile_sort": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "gcd_pairs_workspace_bytes": (_sz, [_i64, _i32]),
     "gcd_pairs_from_table": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gcd_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),

@@ -41,3 +41,25 @@ def set_kmap_search(kind: str) -> None:
 
 def get_kmap_search() -> str:
     return _state["kmap"]
+
+
+# Tile sort of the 3x3x3 neighbour tables for the tcgen05 convolution (csrc/tilesort.cuh): columns sorted by the mask of
+# present neighbours so that a 128-column tile visits 8-12 kernel offsets instead of 21-25.  Opt-in until it has run on a
+# B200 (tests/test_gpu_zz_tilesort.py); maps with fewer rows than ``tile_sort_min_rows`` are left in scan order (the
+# sort is ~20 small launches per map).
+_state["tile_sort"] = os.environ.get("GCDLSS_TILE_SORT", "0") not in ("0", "")
+_state["tile_sort_min_rows"] = int(os.environ.get("GCDLSS_TILE_SORT_MIN_ROWS", "16384"))
+
+
+def set_tile_sort(enabled: bool, min_rows: int | None = None) -> None:
+    _state["tile_sort"] = bool(enabled)
+    if min_rows is not None:
+        _state["tile_sort_min_rows"] = int(min_rows)
+
+
+def get_tile_sort() -> bool:
+    return _state["tile_sort"]
+
+
+def tile_sort_min_rows() -> int:
+    return _state["tile_sort_min_rows"]

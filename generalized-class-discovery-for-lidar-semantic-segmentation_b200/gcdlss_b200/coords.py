@@ -37,6 +37,27 @@ class KernelMap:
         self._mgr = weakref.ref(manager)
         self._back_key, self.back_mirror = back_key, back_mirror
         self._pairs = None
+        self._sorted = None          # (tile-sorted table, its column -> output row permutation), built on first use
+
+    def tc_table(self):
+        """(table, out_rows) for the tcgen05 convolution: the tile-sorted copy when tile sorting is on and this is a
+        3x3x3 map with enough rows to pay for the sort, else (nbr, None).  Pair lists always come from ``nbr``."""
+        if self.nbr is None or self.kv != 27 or not config.get_tile_sort() or self.n_out < config.tile_sort_min_rows():
+            return self.nbr, None
+        if self._sorted is None:
+            self._sorted = ops.kmap_tile_sort(self.nbr)
+        return self._sorted
+
+    def tc_back_table(self):
+        """The same for the table that drives the matching dgrad."""
+        if self._back_key is None:
+            return None, None
+        if self._back_key == "self":
+            return self.tc_table()
+        mgr = self._mgr()
+        if mgr is None:
+            raise RuntimeError("the coordinate manager of this kernel map no longer exists")
+        return mgr.kernel_map(*self._back_key).tc_table()
 
     @property
     def pairs(self):
@@ -106,6 +127,7 @@ class CoordinateManager:
             km = self.kernel_map(*key)
             if with_pairs and km.nbr is not None and km.kv <= 27:
                 km.pairs
+            km.tc_table()            # no-op unless tile sorting is on
         return self
 
     def device_tensors(self):
@@ -123,6 +145,8 @@ class CoordinateManager:
                 out.append(km.nbr)
             if km._pairs is not None:
                 out += list(km._pairs)
+            if km._sorted is not None:
+                out += list(km._sorted)
         return out
 
     # -- kernel maps -----------------------------------------------------------------------

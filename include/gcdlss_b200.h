@@ -139,6 +139,14 @@ int32_t gcd_runtable_build(const int32_t* coords, int64_t n, int32_t ts, void* s
 int32_t gcd_kmap_subm_runs(const int32_t* coords, int64_t n, const void* slots, int64_t cap,
                            int32_t kernel_size, int32_t ts, int32_t* nbr, void* stream);
 
+/* Tile sort of a 3x3x3 table for the tcgen05 convolution (opt-in, GCDLSS_TILE_SORT=1): columns sorted (stably) by the
+ * 27-bit mask of present neighbours, rarest offsets in the top bits, so that the 128-column tiles of the kernel see
+ * 8-12 offsets with a hit instead of 21-25 (csrc/tilesort.cuh).  nbr_sorted [27][n] = nbr[:, out_rows], out_rows [n] the
+ * permutation; pass both to gcd_conv_forward (nbr = nbr_sorted, out_rows).  Pair lists are still built from nbr. */
+size_t gcd_tile_sort_workspace_bytes(int64_t n);
+int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 size_t gcd_pairs_workspace_bytes(int64_t n_out, int32_t kv);
 /* Per-offset pair lists of a table: pairs of offset k are [pair_off[k], pair_off[k+1]), sorted by
  * output row.  pair_in / pair_out hold up to n_out*kv entries; pair_off is int32 [kv+1] (device). */
@@ -175,6 +183,8 @@ typedef struct {
                             accumulator in the epilogue; tcgen05 path: a gcd_bn_stats pass over the
                             stored tensor issued by the same call */
   int32_t math_mode;     /* gcd_math_mode */
+  const int32_t* out_rows; /* optional (tcgen05 path only): nbr is a tile-sorted table (gcd_kmap_tile_sort) and the
+                              result of table column i is written to row out_rows[i] of out; NULL = row i */
 } gcd_conv_args;
 
 int32_t gcd_conv_forward(const gcd_conv_args* args, void* stream);
@@ -298,6 +308,8 @@ typedef struct {
   double* sums;              /* [2 c_out] zero on entry of gcd_block_backward */
   float* mean; float* invstd;                /* [c_out] each: written by forward, read by backward */
   float* dw; float* dgamma; float* dbeta;    /* zero on entry of backward, accumulated into */
+  const int32_t* out_rows;       /* optional: nbr is tile-sorted (see gcd_conv_args.out_rows); tcgen05 units only */
+  const int32_t* back_out_rows;  /* optional: the same for back_nbr */
 } gcd_convbn;
 
 typedef struct {

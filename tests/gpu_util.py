@@ -57,9 +57,9 @@ class OpChecker:
             return dx, dres, dgamma, dbeta
 
         def conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=0, w_packed=None,
-                         stats=None):
+                         stats=None, out_rows=None):
             out = real_conv_fwd(inp, nbr, w3, n_out, transpose_w=transpose_w, mirror=mirror, bias=bias, out_dtype=out_dtype,
-                                math_mode=math_mode, w_packed=w_packed, stats=stats)
+                                math_mode=math_mode, w_packed=w_packed, stats=stats, out_rows=out_rows)
             kv = w3.shape[0]
             ref = torch.zeros((n_out, out.shape[1]), dtype=torch.float64, device=inp.device)
             x = inp.double()
@@ -72,6 +72,8 @@ class OpChecker:
                     idx = nbr[k].long()
                     o = torch.nonzero(idx >= 0).reshape(-1)
                     ref.index_add_(0, o, x[idx[o]] @ b)
+            if out_rows is not None:        # tile-sorted table: column i of the table is output row out_rows[i]
+                ref = torch.zeros_like(ref).index_copy_(0, out_rows.long(), ref)
             if bias is not None:
                 ref += bias.double()
             rec.append(("dgrad" if transpose_w else "fwd", tuple(inp.shape) + tuple(w3.shape), rel(out, ref)))

@@ -1,0 +1,123 @@
+"""Tile sort of the 3x3x3 neighbour tables (csrc/tilesort.cuh, opt-in GCDLSS_TILE_SORT=1).
+
+* the per-thread device code (key, permute), compiled unchanged by g++ (tests/emu/tilesort_emu.cpp), against numpy;
+* the property the convolution relies on: gathering through the sorted table and scattering through ``out_rows`` gives
+  the same result as the table in scan order (checked with the CPU oracle's sparse convolution);
+* what the sort buys on synthetic sweeps: kernel offsets with a hit per 128-column tile, share of real rows.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, small_cloud
+from oracle import conv as oc
+from oracle import coords as ocd
+from oracle import quantize as oq
+
+CSRC = os.path.join(ROOT, "generalized-class-discovery-for-lidar-semantic-segmentation_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="session")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("emu") / "libtilesort_emu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, "-o", out, os.path.join(EMU, "tilesort_emu.cpp")],
+                   check=True, capture_output=True)
+    return C.CDLL(out)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def bit_order():
+    """bit[k] of offset k: offsets ranked by (number of non-zero components, k) -- centre lowest, corners on top."""
+    offs = ocd.kernel_offsets(3)
+    cls = (offs != 0).sum(1)
+    rank = np.lexsort((np.arange(27), cls))
+    bit = np.empty(27, np.int64)
+    bit[rank] = np.arange(27)
+    return bit
+
+
+def sort_reference(nbr_cols):
+    """nbr_cols [27, n] -> (sorted table, rows, keys) in numpy."""
+    valid = (nbr_cols >= 0).astype(np.uint64)
+    keys = (valid << bit_order().astype(np.uint64)[:, None]).sum(0)
+    rows = np.argsort(keys, kind="stable").astype(np.int32)
+    return nbr_cols[:, rows], rows, keys[rows]
+
+
+def emu_sort(emu, nbr_cols):
+    nbr_cols = np.ascontiguousarray(nbr_cols, np.int32)
+    kv, n = nbr_cols.shape
+    out = np.full_like(nbr_cols, -9)
+    rows = np.full(max(n, 1), -9, np.int32)
+    keys = np.zeros(max(n, 1), np.uint64)
+    emu.emu_kmap_tile_sort(_ptr(nbr_cols), C.c_int64(n), C.c_int32(kv), _ptr(out), _ptr(rows), _ptr(keys))
+    return out, rows[:n], keys[:n]
+
+
+def test_bit_order(emu):
+    bits = [emu.emu_tile_sort_bit(k) for k in range(27)]
+    assert bits == list(bit_order())
+    assert bits[13] == 0 and sorted(bits) == list(range(27))                 # centre lowest; a permutation of 0..26
+    offs = ocd.kernel_offsets(3)
+    assert all(bits[k] >= 19 for k in range(27) if (offs[k] != 0).all())       # the eight corners take the top bits
+
+
+@pytest.mark.parametrize("seed,n,ts", [(0, 1, 1), (1, 77, 1), (2, 3000, 1), (3, 2500, 2), (4, 129, 8)])
+def test_emulated_sort_equals_numpy(emu, seed, n, ts):
+    c = small_cloud(seed, n, spread=0.4, batch=seed % 2)
+    c[:, 1:] *= ts
+    nbr = np.ascontiguousarray(ocd.kmap_subm(c, 3, ts).T)
+    got, rows, keys = emu_sort(emu, nbr)
+    ref, ref_rows, ref_keys = sort_reference(nbr)
+    np.testing.assert_array_equal(rows, ref_rows)
+    np.testing.assert_array_equal(keys, ref_keys)
+    np.testing.assert_array_equal(got, ref)
+    assert sorted(rows.tolist()) == list(range(nbr.shape[1]))
+
+
+def test_sorted_table_gives_the_same_convolution(emu):
+    # what conv_fwd_tc_kernel<.., kPerm> does: gather through the sorted table, write column i to row out_rows[i]
+    c = small_cloud(11, 1500, spread=0.35, batch=0)
+    nbr = ocd.kmap_subm(c, 3, 1)                                             # [n, 27]
+    n = nbr.shape[0]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 8, dtype=torch.float64, generator=g)
+    w = torch.randn(27, 8, 5, dtype=torch.float64, generator=g)
+    ref = oc.conv_table(x, nbr, w)
+    sorted_cols, rows, _ = emu_sort(emu, np.ascontiguousarray(nbr.T))
+    out_sorted = oc.conv_table(x, np.ascontiguousarray(sorted_cols.T), w)  # row i of this is output row rows[i]
+    out = torch.empty_like(ref)
+    out[torch.from_numpy(rows.astype(np.int64))] = out_sorted
+    torch.testing.assert_close(out, ref, rtol=0, atol=1e-12)
+
+
+def tile_stats(nbr_cols, tile=128):
+    kv, n = nbr_cols.shape
+    pad = (-n) % tile
+    v = np.concatenate([nbr_cols >= 0, np.zeros((kv, pad), bool)], 1).reshape(kv, -1, tile)
+    active = v.any(2)                                                        # [kv, tiles]
+    return active.sum(0).mean(), v.sum() / (active.sum() * tile)
+
+
+def test_what_the_sort_buys_on_synthetic_sweeps(emu):
+    from gcdlss_b200 import synth
+    for kind, q, n_scans in (("kitti", 0.05, 1), ("nuscenes", 0.1, 2)):
+        scans = [oq.sparse_quantize_me(synth.make_scan(kind, i)[0], q)[0] for i in range(n_scans)]
+        lv = ocd.CoordLevels(oq.batched_coordinates(scans))
+        for level in (0, 1):
+            nbr = np.ascontiguousarray(lv.subm(level, 3).T)
+            a0, r0 = tile_stats(nbr)
+            a1, r1 = tile_stats(emu_sort(emu, nbr)[0])
+            print(f"{kind} level {level}: {nbr.shape[1]} rows; offsets per tile {a0:.1f} -> {a1:.1f}, real rows {100 * r0:.0f} % -> {100 * r1:.0f} %")
+            assert a1 < 0.6 * a0 and r1 > 1.8 * r0

@@ -28,9 +28,9 @@ def bn_backward(dy, x, y, mean, invstd, gamma, relu, training, need_dres):
                 rel(dres, g) if dres is not None else 0.0))
     return dx, dres, dgamma, dbeta
 
-def conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=0, w_packed=None, stats=None):
+def conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=0, w_packed=None, stats=None, out_rows=None):
     out = real_conv_fwd(inp, nbr, w3, n_out, transpose_w=transpose_w, mirror=mirror, bias=bias, out_dtype=out_dtype, math_mode=math_mode,
-                        w_packed=w_packed, stats=stats)
+                        w_packed=w_packed, stats=stats, out_rows=out_rows)
     kv = w3.shape[0]
     ref = torch.zeros((n_out, out.shape[1]), dtype=torch.float64, device=inp.device)
     x = inp.double()
@@ -43,6 +43,7 @@ def conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, bias=N
             idx = nbr[k].long()
             o = torch.nonzero(idx >= 0).reshape(-1)
             ref.index_add_(0, o, x[idx[o]] @ B)
+    if out_rows is not None: ref = torch.zeros_like(ref).index_copy_(0, out_rows.long(), ref)
     if bias is not None: ref += bias.double()
     log.append(("dgrad" if transpose_w else "fwd", tuple(inp.shape), tuple(w3.shape), inp.is_contiguous(), inp.stride(), rel(out, ref)))
     return out

@@ -5,6 +5,7 @@
 #   GCDLSS_KMAP=runs    kernel-map search over x-runs (csrc/runtable.cuh)          -> default if parity + faster
 #   GCD_PAIRS_FUSED=1   pair lists straight from the table, 2 passes instead of 8 (csrc/scan.cu) -> default if parity + faster
 #   GCD_GATHER_FLAT=1   devoxelise gather: float4 elements dealt flat, 4 chains per thread (csrc/gather_rows.cuh)
+#   GCDLSS_TILE_SORT=1  forward/dgrad conv on tile-sorted 3x3x3 tables (csrc/tilesort.cuh): 2.2-2.6x fewer stages -> default if parity + faster
 #   GCD_TC_COMPACT=1    forward/dgrad conv: compacted row copies (csrc/conv_tc.cu) -> default if parity + faster
 mkdir -p gpurun_out
 run() { name=$1; shift; timeout "$1" "${@:2}" > gpurun_out/r2_$name.log 2>&1; echo "$name rc=$?"; tail -3 gpurun_out/r2_$name.log; }
@@ -17,6 +18,9 @@ GCDLSS_KMAP=runs   run bench_runs    600 python bench.py --steps 20 --warmup 5 -
 GCD_PAIRS_FUSED=1  run tests_pairs   600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_conv.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_GATHER_FLAT=1  run tests_gather  600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_mmdet_path.py tests/test_gpu_stage2.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_PAIRS_FUSED=1 GCD_GATHER_FLAT=1 run maps_optin 300 python tools/bench_maps.py
+GCDLSS_TILE_SORT=1 GCDLSS_MATH=bf16 run tests_tilesort 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py tests/test_gpu_stage2.py -m gpu -q --timeout 300 --timeout-method thread
+GCDLSS_TILE_SORT=1 run bench_tilesort 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+GCDLSS_TILE_SORT=1 GCD_TC_COMPACT=1 run bench_tilesort_compact 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 GCD_TC_COMPACT=1   run tests_compact 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_TC_COMPACT=1   run layers_compact 300 python tools/diag_tc.py
 run layers_default 300 python tools/diag_tc.py

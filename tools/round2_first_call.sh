@@ -18,7 +18,7 @@ GCDLSS_KMAP=runs   run bench_runs    600 python bench.py --steps 20 --warmup 5 -
 GCD_PAIRS_FUSED=1  run tests_pairs   600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_conv.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_GATHER_FLAT=1  run tests_gather  600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_mmdet_path.py tests/test_gpu_stage2.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_PAIRS_FUSED=1 GCD_GATHER_FLAT=1 run maps_optin 300 python tools/bench_maps.py
-GCDLSS_TILE_SORT=1 GCDLSS_MATH=bf16 run tests_tilesort 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py tests/test_gpu_stage2.py -m gpu -q --timeout 300 --timeout-method thread
+GCDLSS_TILE_SORT=1 GCDLSS_TILE_SORT_MIN_ROWS=1 run tests_tilesort 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py tests/test_gpu_stage2.py -m gpu -q --timeout 300 --timeout-method thread
 GCDLSS_TILE_SORT=1 run bench_tilesort 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 GCDLSS_TILE_SORT=1 GCD_TC_COMPACT=1 run bench_tilesort_compact 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 GCD_TC_COMPACT=1   run tests_compact 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread

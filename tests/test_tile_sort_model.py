@@ -121,3 +121,50 @@ def test_what_the_sort_buys_on_synthetic_sweeps(emu):
             a1, r1 = tile_stats(emu_sort(emu, nbr)[0])
             print(f"{kind} level {level}: {nbr.shape[1]} rows; offsets per tile {a0:.1f} -> {a1:.1f}, real rows {100 * r0:.0f} % -> {100 * r1:.0f} %")
             assert a1 < 0.6 * a0 and r1 > 1.8 * r0
+
+
+def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
+    # host logic of coords.KernelMap.tc_table / tc_back_table (no GPU: the sort itself is the emulated one)
+    import gcdlss_b200
+    from gcdlss_b200 import coords, ops
+
+    calls = []
+
+    def fake_sort(nbr):
+        calls.append(nbr.shape)
+        s, rows, _ = emu_sort(emu, nbr.numpy())
+        return torch.from_numpy(s), torch.from_numpy(rows)
+
+    monkeypatch.setattr(ops, "kmap_tile_sort", fake_sort)
+
+    class Manager:                      # stands in for the CoordinateManager (held weakly by its maps)
+        def __init__(self):
+            self.maps = {}
+
+        def kernel_map(self, *key):
+            return self.maps[key]
+
+    c = small_cloud(5, 800, spread=0.3, batch=0)
+    nbr = torch.from_numpy(np.ascontiguousarray(ocd.kmap_subm(c, 3, 1).T))
+    n = nbr.shape[1]
+    mgr = Manager()
+    km3 = coords.KernelMap(nbr, n, n, 27, mgr, "self", True)
+    km_down = coords.KernelMap(torch.zeros((8, 10), dtype=torch.int32), n, 10, 8, mgr, (2, 2, 2, True), False)
+    km_up = coords.KernelMap(torch.zeros((8, n), dtype=torch.int32), 10, n, 8, mgr, (1, 2, 2, False), False)
+    km_1x1 = coords.KernelMap(None, n, n, 1, mgr, None, False)
+    mgr.maps = {(2, 2, 2, True): km_up, (1, 2, 2, False): km_down}
+    try:
+        gcdlss_b200.set_tile_sort(False)
+        assert km3.tc_table() == (km3.nbr, None) and not calls
+        gcdlss_b200.set_tile_sort(True, min_rows=n + 1)
+        assert km3.tc_table()[1] is None and not calls                      # too few rows to pay for the sort
+        gcdlss_b200.set_tile_sort(True, min_rows=1)
+        table, rows = km3.tc_table()
+        assert rows is not None and torch.equal(table, nbr[:, rows.long()]) and len(calls) == 1
+        assert km3.tc_table()[0] is table and len(calls) == 1               # cached
+        assert km3.tc_back_table()[0] is table                              # stride-1 maps are self-transposed
+        assert km_down.tc_table() == (km_down.nbr, None)                    # only 3x3x3 tables are sorted
+        assert km_down.tc_back_table() == (km_up.nbr, None) and km_up.tc_back_table() == (km_down.nbr, None)
+        assert km_1x1.tc_table() == (None, None) and km_1x1.tc_back_table() == (None, None)
+    finally:
+        gcdlss_b200.set_tile_sort(False, min_rows=16384)

@@ -14,6 +14,11 @@ __global__ void __launch_bounds__(kThreads) tile_sort_key_kernel(const int32_t* 
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o < n) tile_sort_key_thread(o, nbr, n, keys, vals);
 }
+__global__ void __launch_bounds__(kThreads) tile_sort_key8_kernel(const int32_t* __restrict__ nbr, int64_t n, unsigned long long* __restrict__ keys,
+                                                                   int32_t* __restrict__ vals) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < n) tile_sort_key8_thread(o, nbr, n, keys, vals);
+}
 __global__ void __launch_bounds__(kThreads) tile_sort_permute_kernel(const int32_t* __restrict__ nbr, int64_t n, int kv,
                                                                       const int32_t* __restrict__ rows, int32_t* __restrict__ sorted) {
   tile_sort_permute_thread((int64_t)blockIdx.x * blockDim.x + threadIdx.x, nbr, n, kv, rows, sorted);
@@ -30,7 +35,7 @@ extern "C" size_t gcd_tile_sort_workspace_bytes(int64_t n) {
 
 extern "C" int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows,
                                       void* workspace, size_t workspace_bytes, void* stream) {
-  GCD_REQUIRE(kv == 27, "gcd_kmap_tile_sort: only 3x3x3 tables (kv = 27) are sorted (got %d)", kv);
+  GCD_REQUIRE(kv == 27 || kv == 8, "gcd_kmap_tile_sort: only 3x3x3 and 2x2x2 tables (kv = 27, 8) are sorted (got %d)", kv);
   GCD_REQUIRE(n >= 0 && n * (int64_t)kv < (1ll << 31), "gcd_kmap_tile_sort: table too large");
   GCD_REQUIRE(nbr && nbr_sorted && out_rows, "gcd_kmap_tile_sort: null pointer");
   if (workspace_bytes < gcd_tile_sort_workspace_bytes(n)) { set_error("gcd_kmap_tile_sort: workspace too small"); return GCD_ERR_WORKSPACE; }
@@ -38,8 +43,9 @@ extern "C" int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv,
   cudaStream_t st = as_stream(stream);
   char* p = static_cast<char*>(workspace);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(p); p += align_up((size_t)n * 8, 256);
-  tile_sort_key_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(nbr, n, keys, out_rows);
-  const int32_t rc = radix_sort_pairs(reinterpret_cast<uint64_t*>(keys), out_rows, n, 27, p, radix_sort_workspace_bytes(n), st);
+  if (kv == 27) tile_sort_key_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(nbr, n, keys, out_rows);
+  else          tile_sort_key8_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(nbr, n, keys, out_rows);
+  const int32_t rc = radix_sort_pairs(reinterpret_cast<uint64_t*>(keys), out_rows, n, kv, p, radix_sort_workspace_bytes(n), st);
   if (rc != GCD_OK) return rc;
   tile_sort_permute_kernel<<<(unsigned)ceil_div(n * kv, kThreads), kThreads, 0, st>>>(nbr, n, kv, out_rows, nbr_sorted);
   GCD_LAUNCH_CHECK("gcd_kmap_tile_sort");

@@ -1,4 +1,4 @@
-// tilesort.cuh — per-thread bodies of the tile sort of a 3x3x3 neighbour table (tilesort.cu).
+// tilesort.cuh — per-thread bodies of the tile sort of a 3x3x3 (or 2x2x2) neighbour table (tilesort.cu).
 //
 // The forward / dgrad convolution works on tiles of 128 table columns (output rows) and visits a kernel offset only if
 // some column of the tile has a neighbour there.  In scan order almost every offset has a hit in every tile (21-25 of 27
@@ -34,6 +34,16 @@ GCD_DEVFN void tile_sort_key_thread(int64_t o, const int32_t* nbr, int64_t n, un
   unsigned long long key = 0;
 #pragma unroll
   for (int k = 0; k < 27; ++k) key |= (unsigned long long)(nbr[(int64_t)k * n + o] >= 0 ? 1 : 0) << tile_sort_bit(k);
+  keys[o] = key;
+  vals[o] = (int32_t)o;
+}
+
+// 2x2x2 tables (stride-2 and transposed convolutions): bit k of the key = offset k present.  A transposed map has exactly
+// one entry per column, so the sort groups the columns by child position: one offset per tile instead of all eight.
+GCD_DEVFN void tile_sort_key8_thread(int64_t o, const int32_t* nbr, int64_t n, unsigned long long* keys, int32_t* vals) {
+  unsigned long long key = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) key |= (unsigned long long)(nbr[(int64_t)k * n + o] >= 0 ? 1 : 0) << k;
   keys[o] = key;
   vals[o] = (int32_t)o;
 }

@@ -41,8 +41,8 @@ class KernelMap:
 
     def tc_table(self):
         """(table, out_rows) for the tcgen05 convolution: the tile-sorted copy when tile sorting is on and this is a
-        3x3x3 map with enough rows to pay for the sort, else (nbr, None).  Pair lists always come from ``nbr``."""
-        if self.nbr is None or self.kv != 27 or not config.get_tile_sort() or self.n_out < config.tile_sort_min_rows():
+        3x3x3 or 2x2x2 map with enough rows to pay for the sort, else (nbr, None).  Pair lists always come from ``nbr``."""
+        if self.nbr is None or self.kv not in (8, 27) or not config.get_tile_sort() or self.n_out < config.tile_sort_min_rows():
             return self.nbr, None
         if self._sorted is None:
             self._sorted = ops.kmap_tile_sort(self.nbr)

@@ -255,7 +255,7 @@ def kmap_subm_runs(coords: torch.Tensor, table: RunTable, kernel_size: int, ts: 
 
 
 def kmap_tile_sort(nbr: torch.Tensor):
-    """Tile-sorted copy of a 3x3x3 table for the tcgen05 convolution: (nbr_sorted [27, n] = nbr[:, rows], rows [n] int32)."""
+    """Tile-sorted copy of a 3x3x3 / 2x2x2 table for the tcgen05 convolution: (nbr_sorted [kv, n] = nbr[:, rows], rows [n] int32)."""
     kv, n = nbr.shape
     dev = nbr.device
     nbr_sorted = torch.empty_like(nbr)
@@ -263,7 +263,7 @@ def kmap_tile_sort(nbr: torch.Tensor):
     ws_bytes = int(lib().gcd_tile_sort_workspace_bytes(n))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("gcd_kmap_tile_sort", _ptr(nbr), n, kv, _ptr(nbr_sorted), _ptr(rows), _ptr(ws), ws_bytes, _stream())
-    _count(22)
+    _count(22 if kv == 27 else 12)
     return nbr_sorted, rows[:n]
 
 

@@ -139,10 +139,11 @@ int32_t gcd_runtable_build(const int32_t* coords, int64_t n, int32_t ts, void* s
 int32_t gcd_kmap_subm_runs(const int32_t* coords, int64_t n, const void* slots, int64_t cap,
                            int32_t kernel_size, int32_t ts, int32_t* nbr, void* stream);
 
-/* Tile sort of a 3x3x3 table for the tcgen05 convolution (opt-in, GCDLSS_TILE_SORT=1): columns sorted (stably) by the
- * 27-bit mask of present neighbours, rarest offsets in the top bits, so that the 128-column tiles of the kernel see
- * 8-12 offsets with a hit instead of 21-25 (csrc/tilesort.cuh).  nbr_sorted [27][n] = nbr[:, out_rows], out_rows [n] the
- * permutation; pass both to gcd_conv_forward (nbr = nbr_sorted, out_rows).  Pair lists are still built from nbr. */
+/* Tile sort of a 3x3x3 (kv = 27) or 2x2x2 (kv = 8) table for the tcgen05 convolution (opt-in, GCDLSS_TILE_SORT=1):
+ * columns sorted (stably) by the mask of present neighbours (3x3x3: rarest offsets in the top bits), so that the
+ * 128-column tiles of the kernel see 8-12 offsets with a hit instead of 21-25 (2x2x2: 1-4 instead of 7-8)
+ * (csrc/tilesort.cuh).  nbr_sorted [kv][n] = nbr[:, out_rows], out_rows [n] the permutation; pass both to
+ * gcd_conv_forward (nbr = nbr_sorted, out_rows).  Pair lists are still built from nbr. */
 size_t gcd_tile_sort_workspace_bytes(int64_t n);
 int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows,
                            void* workspace, size_t workspace_bytes, void* stream);

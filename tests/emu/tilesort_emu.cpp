@@ -12,7 +12,10 @@ int32_t emu_tile_sort_bit(int32_t k) { return gcd::tile_sort_bit(k); }
 void emu_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows, unsigned long long* keys_out) {
   std::vector<unsigned long long> keys(n);
   std::vector<int32_t> vals(n);
-  for (int64_t o = 0; o < n; ++o) gcd::tile_sort_key_thread(o, nbr, n, keys.data(), vals.data());
+  for (int64_t o = 0; o < n; ++o) {
+    if (kv == 27) gcd::tile_sort_key_thread(o, nbr, n, keys.data(), vals.data());
+    else gcd::tile_sort_key8_thread(o, nbr, n, keys.data(), vals.data());
+  }
   std::vector<int64_t> idx(n);
   std::iota(idx.begin(), idx.end(), 0);
   std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });

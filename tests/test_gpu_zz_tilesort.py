@@ -43,6 +43,18 @@ def test_sort_equals_numpy(cuda, n):
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
 
 
+def test_sort_of_stride2_tables_equals_numpy(cuda):
+    from gcdlss_b200 import ops
+    c = small_cloud(3, 6000, spread=0.5, batch=0)
+    coarse, parent, code = ocd.stride2(c, 1)
+    for nbr in (ocd.kmap_down2(parent, code, coarse.shape[0]), ocd.kmap_up2(parent, code)):
+        cols = np.ascontiguousarray(nbr.T)
+        got, rows = ops.kmap_tile_sort(torch.from_numpy(cols).cuda())
+        ref, ref_rows, _ = sort_reference(cols)
+        np.testing.assert_array_equal(rows.cpu().numpy(), ref_rows)
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 32), (96, 96), (256, 128)])
 def test_conv_forward_and_dgrad_with_sorted_table(cuda, tile_sort, cin, cout):
     from gcdlss_b200 import ops

@@ -48,9 +48,10 @@ def bit_order():
 
 
 def sort_reference(nbr_cols):
-    """nbr_cols [27, n] -> (sorted table, rows, keys) in numpy."""
+    """nbr_cols [27 | 8, n] -> (sorted table, rows, keys) in numpy."""
     valid = (nbr_cols >= 0).astype(np.uint64)
-    keys = (valid << bit_order().astype(np.uint64)[:, None]).sum(0)
+    bits = bit_order() if nbr_cols.shape[0] == 27 else np.arange(8)
+    keys = (valid << bits.astype(np.uint64)[:, None]).sum(0)
     rows = np.argsort(keys, kind="stable").astype(np.int32)
     return nbr_cols[:, rows], rows, keys[rows]
 
@@ -84,6 +85,22 @@ def test_emulated_sort_equals_numpy(emu, seed, n, ts):
     np.testing.assert_array_equal(keys, ref_keys)
     np.testing.assert_array_equal(got, ref)
     assert sorted(rows.tolist()) == list(range(nbr.shape[1]))
+
+
+def test_stride2_tables(emu):
+    # 2x2x2 maps: a transposed (up) map has one entry per column -> exactly one offset per tile after the sort
+    c = small_cloud(21, 4000, spread=0.5, batch=0)
+    coarse, parent, code = ocd.stride2(c, 1)
+    for nbr in (ocd.kmap_down2(parent, code, coarse.shape[0]), ocd.kmap_up2(parent, code)):
+        cols = np.ascontiguousarray(nbr.T)
+        got, rows, keys = emu_sort(emu, cols)
+        ref, ref_rows, ref_keys = sort_reference(cols)
+        np.testing.assert_array_equal(rows, ref_rows)
+        np.testing.assert_array_equal(got, ref)
+        a0, r0 = tile_stats(cols)
+        a1, r1 = tile_stats(got)
+        assert a1 < a0 and r1 > r0
+    assert a1 < 1.3 and r1 > 0.75                                             # the up map
 
 
 def test_sorted_table_gives_the_same_convolution(emu):
@@ -163,8 +180,11 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
         assert rows is not None and torch.equal(table, nbr[:, rows.long()]) and len(calls) == 1
         assert km3.tc_table()[0] is table and len(calls) == 1               # cached
         assert km3.tc_back_table()[0] is table                              # stride-1 maps are self-transposed
-        assert km_down.tc_table() == (km_down.nbr, None)                    # only 3x3x3 tables are sorted
-        assert km_down.tc_back_table() == (km_up.nbr, None) and km_up.tc_back_table() == (km_down.nbr, None)
+        t_down, r_down = km_down.tc_table()                                 # 2x2x2 tables are sorted as well
+        assert r_down is not None and torch.equal(t_down, km_down.nbr[:, r_down.long()])
+        assert km_up.tc_back_table()[0] is t_down and km_down.tc_back_table()[0] is km_up.tc_table()[0]
+        km5 = coords.KernelMap(torch.zeros((125, n), dtype=torch.int32), n, n, 125, mgr, "self", True)
+        assert km5.tc_table() == (km5.nbr, None)                            # the 5x5x5 stem goes through im2col: not sorted
         assert km_1x1.tc_table() == (None, None) and km_1x1.tc_back_table() == (None, None)
     finally:
         gcdlss_b200.set_tile_sort(False, min_rows=16384)

@@ -127,7 +127,8 @@ class CoordinateManager:
             km = self.kernel_map(*key)
             if with_pairs and km.nbr is not None and km.kv <= 27:
                 km.pairs
-            km.tc_table()            # no-op unless tile sorting is on
+            if config.get_math_mode() == "bf16":
+                km.tc_table()        # tile-sorted copy for the tcgen05 convolution; no-op unless tile sorting is on
         return self
 
     def device_tensors(self):

@@ -12,9 +12,11 @@ run() { name=$1; shift; timeout "$1" "${@:2}" > gpurun_out/r2_$name.log 2>&1; ec
 run tests          900 python -m pytest tests -m gpu -q --timeout 300 --timeout-method thread
 run smoke          300 python -c "import __graft_entry__ as g; g.smoke()"
 run maps           300 python tools/bench_maps.py
-run bench_default  600 python bench.py --steps 20 --warmup 5
+run bench_default  900 python bench.py --steps 20 --warmup 5      # tile sort decided by the self-check (its verdict is in config.tile_sort)
+GCDLSS_TILE_SORT=0 run bench_scan_order 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+run selfcheck      300 python tools/selfcheck_tilesort.py 0
 GCDLSS_KMAP=runs   run tests_runs    600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
-GCDLSS_KMAP=runs   run bench_runs    600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+GCDLSS_TILE_SORT=0 GCDLSS_KMAP=runs   run bench_runs    600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 GCD_PAIRS_FUSED=1  run tests_pairs   600 python -m pytest tests/test_gpu_coords.py tests/test_gpu_conv.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_GATHER_FLAT=1  run tests_gather  600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_mmdet_path.py tests/test_gpu_stage2.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_PAIRS_FUSED=1 GCD_GATHER_FLAT=1 run maps_optin 300 python tools/bench_maps.py
@@ -24,9 +26,9 @@ GCDLSS_TILE_SORT=1 GCD_TC_COMPACT=1 run bench_tilesort_compact 600 python bench.
 GCD_TC_COMPACT=1   run tests_compact 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_fused_block.py tests/test_gpu_minkunet.py -m gpu -q --timeout 300 --timeout-method thread
 GCD_TC_COMPACT=1   run layers_compact 300 python tools/diag_tc.py
 run layers_default 300 python tools/diag_tc.py
-GCD_TC_COMPACT=1   run bench_compact 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+GCDLSS_TILE_SORT=0 GCD_TC_COMPACT=1   run bench_compact 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 ( cd tools/ubench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../generalized-class-discovery-for-lidar-semantic-segmentation_b200/csrc -o smem_port smem_port.cu ) > /dev/null 2>&1
 run smem_port      120 tools/ubench/smem_port
 # fresh launch list of the default path (fixed warm-up so --launch-skip lands inside the timed region)
-GCDLSS_BENCH_FIXED_WARMUP=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 4000 -c 1800 --csv \
+GCDLSS_TILE_SORT=0 GCDLSS_BENCH_FIXED_WARMUP=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 4000 -c 1800 --csv \
   --log-file gpurun_out/r2_launches.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2_ncu.log 2>&1; echo "ncu rc=$?"

@@ -103,7 +103,7 @@ def tile_sort_selfcheck(local_rank, scans_per_gpu, kind, n_classes):
     wrong -- a failed check, a device fault, a hang -- happens in the child and reads as "leave it off"."""
     cmd = [sys.executable, os.path.join(ROOT, "tools", "selfcheck_tilesort.py"), str(local_rank), str(scans_per_gpu), kind, str(n_classes)]
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)     # well inside the 180 s NCCL timeout of the ranks waiting for the verdict
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if not lines:
             return {"ok": False, "reason": f"self-check printed no verdict (exit code {r.returncode}): {r.stderr[-300:]}"}

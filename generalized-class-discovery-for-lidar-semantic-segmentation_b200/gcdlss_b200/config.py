@@ -26,7 +26,7 @@ def get_math_mode() -> str:
 # Kernel-map search of the stride-1 convolutions.  "points": one hash slot per voxel (gcd_hash_build + gcd_kmap_subm).
 # "runs": one 32-byte slot per run of four x-adjacent cells (gcd_runtable_build + gcd_kmap_subm_runs, csrc/runtable.cuh):
 # the same maps from 2.4-2.8x fewer scattered loads.  The run table's logic is held to the oracle on the CPU by
-# tests/test_emulated_kernels.py; it becomes the default once tests/test_gpu_zz_runtable.py has passed on a B200.
+# tests/test_emulated_kernels.py; it becomes the default once tests/test_gpu_zzz_runtable.py has passed on a B200.
 _KMAP = ("points", "runs")
 _state["kmap"] = os.environ.get("GCDLSS_KMAP", "points")
 if _state["kmap"] not in _KMAP:

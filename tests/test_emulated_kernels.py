@@ -1,7 +1,7 @@
 """Host emulation of the integer kernels: the per-thread device functions of csrc/runtable.cuh, compiled unchanged by
 g++ (tests/emu/), against the CPU oracle.  Runs without a GPU; the same source is what nvcc builds for sm_100a, so the
 logic of the CUDA path is checked here and only its hardware-specific parts (the 256-bit load, real concurrency) are
-left to tests/test_gpu_zz_runtable.py."""
+left to tests/test_gpu_zzz_runtable.py."""
 import ctypes as C
 import os
 import shutil

@@ -150,6 +150,7 @@ PROTOTYPES = {
     "gcd_rows_gather": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "gcd_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "gcd_csr_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "gcd_consistency_rows": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gcd_block_forward": (_i32, [C.POINTER(BlockArgs), _vp]),
     "gcd_block_backward": (_i32, [C.POINTER(BlockArgs), _vp]),
     "gcd_segment_reduce": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),

@@ -506,3 +506,23 @@ def segment_reduce(x, seg_off, order, n_segments: int, mode: int):
     call("gcd_segment_reduce", _ptr(x), _ld(x), _ptr(seg_off), _ptr(order), n_segments, x.shape[1], mode, _ptr(out), x.shape[1], _stream())
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------ loss side
+def consistency_rows(logits_s: torch.Tensor, logits_t: torch.Tensor, threshold: float = 0.0, want_grad: bool = False):
+    """One pass over two fp32 logit matrices [n, c]: (sq_err [n], max_prob [n], label [n] int64, grad [n, c] or None);
+    see gcd_consistency_rows in include/gcdlss_b200.h."""
+    _require_cuda(logits_s, logits_t)
+    if logits_s.shape != logits_t.shape or logits_s.dim() != 2:
+        raise ValueError("student and teacher logits must be [n, c] of the same shape")
+    ls, lt = _rowmajor(logits_s.float()), _rowmajor(logits_t.float())
+    n, c = ls.shape
+    dev = ls.device
+    sq_err = torch.empty(n, dtype=torch.float32, device=dev)
+    max_prob = torch.empty(n, dtype=torch.float32, device=dev)
+    label = torch.empty(n, dtype=torch.int64, device=dev)
+    grad = torch.empty((n, c), dtype=torch.float32, device=dev) if want_grad else None
+    call("gcd_consistency_rows", ls.data_ptr(), _ld(ls), lt.data_ptr(), _ld(lt), n, c, float(threshold), sq_err.data_ptr(), max_prob.data_ptr(),
+         label.data_ptr(), grad.data_ptr() if grad is not None else None, c, _stream())
+    _count()
+    return sq_err, max_prob, label, grad

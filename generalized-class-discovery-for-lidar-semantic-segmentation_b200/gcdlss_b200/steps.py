@@ -32,6 +32,31 @@ def point_cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index
     return per_point.sum() / (labels != ignore_index).sum().clamp(min=1)
 
 
+class _ConsistencyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits_s, logits_t, threshold):
+        from . import ops
+        sq_err, max_prob, label, grad = ops.consistency_rows(logits_s.detach(), logits_t.detach(), threshold, want_grad=logits_s.requires_grad)
+        n, c = logits_s.shape
+        ctx.save_for_backward(grad)
+        ctx.numel, ctx.in_dtype = n * c, logits_s.dtype
+        ctx.mark_non_differentiable(max_prob, label)
+        return sq_err.sum() / (n * c), max_prob, label
+
+    @staticmethod
+    def backward(ctx, g_mse, _g_prob, _g_label):
+        (grad,) = ctx.saved_tensors
+        return (grad * (g_mse / ctx.numel)).to(ctx.in_dtype), None, None
+
+
+def consistency_terms(logits_s: torch.Tensor, logits_t: torch.Tensor, threshold: float = 0.0):
+    """(F.mse_loss(softmax(logits_s), softmax(logits_t)), max teacher probability [n], teacher argmax [n]) from one pass
+    over the two logit matrices (gcd_consistency_rows; ref modules/exp_merge_mean_teacher.py:2832-2850).  Differentiable
+    with respect to ``logits_s`` only (the reference detaches the teacher); labels are -1 where the teacher's maximum
+    probability is below ``threshold`` (0 = keep all)."""
+    return _ConsistencyFunction.apply(logits_s, logits_t, float(threshold))
+
+
 def stage1_step(model, feats, bcoords, labels):
     st = SparseTensor(features=feats.float(), coordinates=bcoords.int())
     out = model(st)
@@ -60,10 +85,11 @@ def laser_mix(points_sup, points_unsup, feats_sup, feats_unsup, labels_sup, labe
 
 class Stage2Harness:
     def __init__(self, student, teacher, optimizer, voxel_size: float, mse_coeff: float = 200.0, ema_momentum: float = 0.01,
-                 num_areas=(3, 4, 5, 6), reducer=None):
+                 num_areas=(3, 4, 5, 6), reducer=None, fused_loss: bool = False):
         self.student, self.teacher, self.opt = student, teacher, optimizer
         self.voxel_size, self.mse_coeff, self.ema_momentum, self.num_areas = voxel_size, mse_coeff, ema_momentum, num_areas
         self.reducer = reducer
+        self.fused_loss = fused_loss      # consistency terms through gcd_consistency_rows (one pass) instead of torch ops
         self._step = 0
         for p in self.teacher.parameters():
             p.requires_grad_(False)                                        # ref :155, :251-254
@@ -83,10 +109,14 @@ class Stage2Harness:
         out_s = self.student(st)
         n_sup = sup["coords"].shape[0]
         loss = point_cross_entropy(out_s["logits"][:n_sup], sup["labels"].long())
-        prob_s = F.softmax(out_s["logits"][n_sup:], dim=1)
-        prob_t = F.softmax(out_t["logits"][n_sup:], dim=1)
-        loss = loss + F.mse_loss(prob_s, prob_t.detach()) * self.mse_coeff
-        max_prob_t, target_t = torch.max(prob_t, dim=1)
+        if self.fused_loss:
+            mse, max_prob_t, target_t = consistency_terms(out_s["logits"][n_sup:], out_t["logits"][n_sup:])
+            loss = loss + mse * self.mse_coeff
+        else:
+            prob_s = F.softmax(out_s["logits"][n_sup:], dim=1)
+            prob_t = F.softmax(out_t["logits"][n_sup:], dim=1)
+            loss = loss + F.mse_loss(prob_s, prob_t.detach()) * self.mse_coeff
+            max_prob_t, target_t = torch.max(prob_t, dim=1)
         # voxel -> point devoxelisation of the pseudo labels.  The reference concatenates the scans' inverse maps without
         # offsetting the second by the first scan's voxel count (ref :2787-2790); preserved, not fixed.
         inv_cat = torch.cat(unsup["inverse_maps"])

@@ -285,6 +285,16 @@ int32_t gcd_csr_build(const int64_t* idx, int64_t n_points, int64_t n_segments, 
 int32_t gcd_segment_reduce(const float* in, int64_t ld_in, const int32_t* seg_off, const int32_t* order,
                            int64_t n_segments, int32_t c, int32_t mode, float* out, int64_t ld_out, void* stream);
 
+/* ------------------------------------------------------------------ loss side ----------- */
+/* Teacher/student consistency terms of the Stage-2 step on fp32 voxel logits [n, c], one pass (SURVEY 8(f) rank 3;
+ * replaces F.softmax x2 + F.mse_loss + torch.max, ref modules/exp_merge_mean_teacher.py:2832-2850):
+ *   sq_err[i] = sum_c (softmax(logits_s[i])_c - softmax(logits_t[i])_c)^2      (mse_loss = sum_i sq_err[i] / (n c))
+ *   max_prob[i], label[i] = max / first argmax of softmax(logits_t[i]); label = -1 where max_prob < threshold (> 0)
+ *   grad (optional, [n, c]) = d sq_err[i] / d logits_s[i, :]. */
+int32_t gcd_consistency_rows(const float* logits_s, int64_t ld_s, const float* logits_t, int64_t ld_t, int64_t n, int32_t c,
+                             float threshold, float* sq_err, float* max_prob, int64_t* label, float* grad, int64_t ld_g,
+                             void* stream);
+
 /* ------------------------------------------------------------------ fused blocks -------- */
 /* conv -> batch norm (-> ReLU) triples and whole residual blocks sequenced from C: one call per block and
  * direction instead of one per launch (the step is launch-bound from Python).  Replaces, as one unit,

@@ -187,3 +187,41 @@ def test_flat_gather_is_a_row_copy(emu_gather, n_in, n_out, c, pad_in, pad_out):
     emu_gather.emu_rows_gather_flat(_ptr(src), C.c_int64(c + pad_in), _ptr(idx), C.c_int64(n_out), C.c_int32(c), _ptr(out), C.c_int64(c + pad_out))
     np.testing.assert_array_equal(out[:n_out, :c], src[idx][:, :c])
     assert (out[:n_out, c:] == -3.0).all() and (out[n_out:] == -3.0).all()
+
+
+@pytest.fixture(scope="session")
+def emu_loss(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("emu") / "libloss_emu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, "-o", out, os.path.join(EMU, "loss_emu.cpp")],
+                   check=True, capture_output=True)
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("n,c,scale", [(1, 2, 1.0), (257, 17, 3.0), (1000, 20, 8.0), (64, 3, 0.01)])
+def test_consistency_rows_against_torch(emu_loss, n, c, scale):
+    # gcd_consistency_rows (csrc/loss_rows.cuh) vs softmax / mse_loss / max of torch, forward and gradient
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(n + c)
+    ls = (torch.randn(n, c, generator=g) * scale).requires_grad_(True)
+    lt = torch.randn(n, c, generator=g) * scale
+    lt[0, :] = lt[0, 0]                                            # a tie: the first maximum wins
+    ps, pt = F.softmax(ls, 1), F.softmax(lt, 1)
+    ref_sq = ((ps - pt) ** 2).sum(1)
+    ref_prob, ref_label = torch.max(pt, 1)
+    ref_sq.sum().backward()
+    sq = np.zeros(n, np.float32); mp = np.zeros(n, np.float32); lab = np.zeros(n, np.int64); grad = np.zeros((n, c), np.float32)
+    a, b = ls.detach().numpy().copy(), lt.numpy().copy()
+    emu_loss.emu_consistency_rows(_ptr(a), C.c_int64(c), _ptr(b), C.c_int64(c), C.c_int64(n), C.c_int32(c), C.c_float(0.9), _ptr(sq), _ptr(mp),
+                                  _ptr(lab), _ptr(grad), C.c_int64(c))
+    np.testing.assert_allclose(sq, ref_sq.detach().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(mp, ref_prob.numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(grad, ls.grad.numpy(), rtol=1e-4, atol=2e-6)      # fp32 cancellation noise of both sides
+    expect = np.where(ref_prob.numpy() < 0.9, -1, ref_label.numpy())
+    sure = np.abs(ref_prob.numpy() - 0.9) > 1e-6                   # rows within rounding of the threshold may fall either way
+    np.testing.assert_array_equal(lab[sure], expect[sure])
+    assert lab[0] in (-1, 0)
+    # mse_loss itself
+    assert abs(sq.sum() / (n * c) - float(F.mse_loss(ps, pt))) < 1e-6

@@ -106,3 +106,27 @@ def test_model_forward_is_identical_in_both_modes(cuda):
         finally:
             gcdlss_b200.set_kmap_search("points")
     assert torch.equal(outs[0], outs[1])
+
+
+# ---- fused consistency terms (gcd_consistency_rows): same file because it is as new as the run table
+@pytest.mark.parametrize("n,c", [(1, 2), (4099, 17), (200000, 20)])
+def test_consistency_terms_against_torch(cuda, n, c):
+    import torch.nn.functional as F
+    from gcdlss_b200.steps import consistency_terms
+    g = torch.Generator(device="cuda").manual_seed(n)
+    ls = (torch.randn(n, c, device="cuda", generator=g) * 3).requires_grad_(True)
+    lt = torch.randn(n, c, device="cuda", generator=g) * 3
+    mse, prob, label = consistency_terms(ls, lt, threshold=0.9)
+    (mse * 200.0).backward()
+    got_grad = ls.grad.clone()
+    ls.grad = None
+    ps, pt = F.softmax(ls, 1), F.softmax(lt, 1)
+    ref = F.mse_loss(ps, pt)
+    (ref * 200.0).backward()
+    ref_prob, ref_label = torch.max(pt, 1)
+    assert abs(float(mse) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+    torch.testing.assert_close(prob, ref_prob, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(got_grad, ls.grad, rtol=1e-4, atol=1e-7 + 1e-5 * float(ls.grad.abs().max()))
+    sure = (ref_prob - 0.9).abs() > 1e-6
+    expect = torch.where(ref_prob < 0.9, torch.full_like(ref_label, -1), ref_label)
+    assert torch.equal(label[sure], expect[sure])

@@ -224,4 +224,4 @@ def test_consistency_rows_against_torch(emu_loss, n, c, scale):
     np.testing.assert_array_equal(lab[sure], expect[sure])
     assert lab[0] in (-1, 0)
     # mse_loss itself
-    assert abs(sq.sum() / (n * c) - float(F.mse_loss(ps, pt))) < 1e-6
+    assert abs(sq.sum() / (n * c) - float(F.mse_loss(ps, pt).detach())) < 1e-6

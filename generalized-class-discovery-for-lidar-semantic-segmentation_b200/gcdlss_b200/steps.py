@@ -36,7 +36,7 @@ class _ConsistencyFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits_s, logits_t, threshold):
         from . import ops
-        sq_err, max_prob, label, grad = ops.consistency_rows(logits_s.detach(), logits_t.detach(), threshold, want_grad=logits_s.requires_grad)
+        sq_err, max_prob, label, grad = ops.consistency_rows(logits_s.detach(), logits_t.detach(), threshold, want_grad=ctx.needs_input_grad[0])
         n, c = logits_s.shape
         ctx.save_for_backward(grad)
         ctx.numel, ctx.in_dtype = n * c, logits_s.dtype

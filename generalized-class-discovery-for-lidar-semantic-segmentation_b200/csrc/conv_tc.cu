@@ -83,9 +83,8 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
 // kNQ = number of 64-channel slices of Cin when known at compile time (1, 2, 3, 4, 6), 0 = runtime loop.
 // With kNQ known the slice loop is unrolled and every copy uses an immediate offset from a per-offset base
 // pointer, which is what keeps the producer loop at a few dozen instructions per stage.
-// kCompact (opt-in, GCD_TC_COMPACT=1, not yet measured on hardware): the owner copies only the rows that need touching.
-// kPerm (opt-in, tile-sorted tables): table column i is output row p.out_rows[i]; only the epilogue's store address changes.
-template <int kNQ, bool kCompact = false, bool kPerm = false>
+// kPerm (tile-sorted tables, tilesort.cu): table column i is output row p.out_rows[i]; only the epilogue's store address changes.
+template <int kNQ, bool kPerm = false>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is at least 16-byte aligned; the swizzle pattern needs 1024.
@@ -160,9 +159,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     uint32_t st = grp, ph = 0;                 // stage / parity of this group's next owned iteration
     int own_skip = grp < PA ? grp : 0x7fffffff;     // iterations until the next owned one
     uint32_t tile_seq = 0;
-    // kCompact: rows of this group's slot (PA == stages: a group always fills the same slot) that hold something other than
-    // zeros, one bit per row, 32 rows per word.  Unknown at start, so the first fill touches every row.
-    uint32_t dirty[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 #ifdef GCD_TC_PROFILE
     long long prof_wait = 0, prof_iters = 0, prof_table = 0; const long long prof_t0 = clock64();
 #endif
@@ -207,39 +203,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #ifdef GCD_TC_PROFILE
           if (!(p.ablate & 2))
 #endif
-          if constexpr (kCompact) {
-            // Only rows that hold a neighbour now (copy) or held one in the slot's previous use (zero fill) are touched,
-            // packed four to a warp-level copy: absent neighbours (66-80 % of the table) cost no shared-memory write.
-            // Data copies of a partial last slice are issued by the lanes of its valid chunks only; zero fills always by
-            // all eight chunk lanes, so a clean row is zero across the full 128 bytes whatever slice used the slot last.
-            const uint32_t a_stage = a_base + st * kABytes;
-            const char* src_q = col_base + q * (kChunkK * 2);
-            const bool full_width = q + 1 < nq || last_active;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              if ((w * G) >> 2 != sub) continue;              // the warp's share of the rows: 4 / G words of 32
-              const int v = lds_s32(s_nbr_addr + (uint32_t)(k * kTileM + w * 32 + lane) * 4u);   // entry of row 32 w + lane
-              const uint32_t valid = __ballot_sync(0xffffffffu, v >= 0);
-              uint32_t touch = valid | dirty[w];
-              dirty[w] = valid;
-#pragma unroll 1
-              while (touch) {                                  // warp-uniform trip count: ceil(popc(touch) / 4)
-                int bit = -1;                                  // the (rsub)-th lowest set bit of touch, -1 if there are fewer
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const int b = __ffs(touch) - 1;              // -1 once touch is exhausted
-                  if (g == rsub) bit = b;
-                  touch &= touch - 1;                          // 0 stays 0
-                }
-                const int r = __shfl_sync(0xffffffffu, v, bit & 31);
-                const uint32_t row = (uint32_t)(w * 32 + (bit & 31));
-                const uint32_t dst = a_stage + (row >> 3) * 1024u + (row & 7u) * (uint32_t)kRowBytes + (((uint32_t)chunk ^ (row & 7u)) << 4);
-                const bool copy = r >= 0;
-                cp_async_16_pred(dst, src_q + (uint64_t)(uint32_t)max(r, 0) * ld_bytes, copy ? 16u : 0u,
-                                 (bit >= 0 && (full_width || !copy)) ? 1u : 0u);
-              }
-            }
-          } else
           if (q + 1 < nq || last_active) {
             const uint32_t nb = s_nbr_addr + (uint32_t)(k * kTileM + rsub) * 4u;
             const uint32_t a_stage = a_base + st * kABytes;
@@ -733,15 +696,15 @@ bool conv_forward_tc_supported(const gcd_conv_args* a) {
 }
 
 using FwdKernel = void (*)(const FwdParams);
-template <bool kCompact, bool kPerm>
+template <bool kPerm>
 FwdKernel pick_fwd_kernel(int nq) {
   switch (nq) {
-    case 1: return conv_fwd_tc_kernel<1, kCompact, kPerm>;
-    case 2: return conv_fwd_tc_kernel<2, kCompact, kPerm>;
-    case 3: return conv_fwd_tc_kernel<3, kCompact, kPerm>;
-    case 4: return conv_fwd_tc_kernel<4, kCompact, kPerm>;
-    case 6: return conv_fwd_tc_kernel<6, kCompact, kPerm>;
-    default: return conv_fwd_tc_kernel<0, kCompact, kPerm>;
+    case 1: return conv_fwd_tc_kernel<1, kPerm>;
+    case 2: return conv_fwd_tc_kernel<2, kPerm>;
+    case 3: return conv_fwd_tc_kernel<3, kPerm>;
+    case 4: return conv_fwd_tc_kernel<4, kPerm>;
+    case 6: return conv_fwd_tc_kernel<6, kPerm>;
+    default: return conv_fwd_tc_kernel<0, kPerm>;
   }
 }
 
@@ -778,12 +741,8 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
 #endif
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;
-  // Compacted row copies (opt-in until measured on a B200): needs a fixed slot per owner group (owner groups == stages).
-  static const bool want_compact = getenv("GCD_TC_COMPACT") && atoi(getenv("GCD_TC_COMPACT")) != 0;
-  const bool compact = want_compact && p.group <= 4 && kProducerWarps / p.group >= stages;
   const int nq_sel = (a->c_in + kChunkK - 1) / kChunkK;
-  const FwdKernel kernel = compact ? (p.out_rows ? pick_fwd_kernel<true, true>(nq_sel) : pick_fwd_kernel<true, false>(nq_sel))
-                                   : (p.out_rows ? pick_fwd_kernel<false, true>(nq_sel) : pick_fwd_kernel<false, false>(nq_sel));
+  const FwdKernel kernel = p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel);
   {
     // opt-in to the large dynamic shared memory once per kernel instantiation (benign race: the call is idempotent)
     static FwdKernel done[32];

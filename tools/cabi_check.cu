@@ -9,7 +9,7 @@
 //   gcd_rows_gather                           == host gather                                (GCD_GATHER_FLAT=1 selects the flat kernel)
 //   gcd_consistency_rows                      == host double-precision softmax / mse / max
 // Prints one line per check and "ALL OK" / "FAILED n".  Run it twice: plain, and with
-//   GCD_PAIRS_FUSED=1 GCD_GATHER_FLAT=1 GCD_TC_COMPACT=1
+//   GCD_PAIRS_FUSED=1 GCD_GATHER_FLAT=1
 // Build (tools/build_cabi_check.sh):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -Iinclude -o tools/cabi_check tools/cabi_check.cu \
 //        -L<pkg>/gcdlss_b200 -lgcdlss_sm100a -Xlinker -rpath -Xlinker '$ORIGIN/../<pkg>/gcdlss_b200'
@@ -68,9 +68,8 @@ static double offsets_per_tile(const std::vector<int32_t>& nbr, int kv, int64_t 
 int main() {
   CK(cudaSetDevice(0));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
-  printf("device: %s, sm_%d%d; GCD_PAIRS_FUSED=%s GCD_GATHER_FLAT=%s GCD_TC_COMPACT=%s\n", prop.name, prop.major, prop.minor,
-         getenv("GCD_PAIRS_FUSED") ? getenv("GCD_PAIRS_FUSED") : "-", getenv("GCD_GATHER_FLAT") ? getenv("GCD_GATHER_FLAT") : "-",
-         getenv("GCD_TC_COMPACT") ? getenv("GCD_TC_COMPACT") : "-");
+  printf("device: %s, sm_%d%d; GCD_PAIRS_FUSED=%s GCD_GATHER_FLAT=%s\n", prop.name, prop.major, prop.minor,
+         getenv("GCD_PAIRS_FUSED") ? getenv("GCD_PAIRS_FUSED") : "-", getenv("GCD_GATHER_FLAT") ? getenv("GCD_GATHER_FLAT") : "-");
   std::mt19937 rng(1234);
   std::uniform_real_distribution<float> uni(0.f, 1.f);
 

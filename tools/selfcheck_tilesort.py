@@ -6,7 +6,8 @@ bench's CUDA context) and switches tile sorting on only if every check passes an
   1. gcd_kmap_tile_sort == a stable torch sort of the presence-mask keys (3x3x3 and 2x2x2 tables), bit exact;
   2. forward and dgrad convolutions through sorted tables against an fp64 re-computation, within the stated bf16 bound;
   3. one training step of the bench's model in both modes: loss and logits agree;
-  4. step time (map build + sort + forward + backward on one stream) of both modes.
+  4. forward + backward time on ready maps in both modes (the bench builds maps and sort on a side stream, one batch
+     ahead); the map-build times are reported next to it.
 
 Prints one JSON line: {"ok": bool, "reason": str, ...}.  Exit code 0 whenever the line was printed."""
 import json
@@ -94,31 +95,43 @@ def main():
     torch.manual_seed(1234)
     model = MinkUNetBase(num_classes=n_classes).to(dev).train()
 
-    def step():
-        model.zero_grad(set_to_none=True)
+    def build():
         st = ME.SparseTensor(features=f, coordinates=bc)
         st.coordinate_manager.prebuild_unet(5, 5, with_pairs=True)
+        return st
+
+    def step(st):
+        model.zero_grad(set_to_none=True)
         logits = model(st)["logits"]
         loss = point_cross_entropy(logits, labels)
         loss.backward()
         return logits.detach().float(), float(loss)
 
-    res = {}
-    for mode in (False, True, False, True):          # interleaved, second pass is the timed one
-        gcdlss_b200.set_tile_sort(mode)
-        for _ in range(3):
-            logits, loss = step()
+    def timed(fn, reps):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
-            step()
+        for _ in range(reps):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        res[mode] = (logits, loss, e0.elapsed_time(e1) / 5)
+        return e0.elapsed_time(e1) / reps
+
+    # The bench builds the maps (and the sort) of batch i + 1 on a side stream while batch i trains, so the step it measures is
+    # the forward + backward on ready maps: that is what is compared here; the cost of the build is reported next to it.
+    res = {}
+    for mode in (False, True, False, True):          # interleaved, the second pass of each mode is the one that counts
+        gcdlss_b200.set_tile_sort(mode)
+        st = build()
+        for _ in range(3):
+            logits, loss = step(st)
+        ms_step = timed(lambda: step(st), 5)
+        ms_build = timed(build, 3)
+        res[mode] = (logits, loss, ms_step, ms_build)
     gcdlss_b200.set_tile_sort(False)
-    (l0, loss0, ms0), (l1, loss1, ms1) = res[False], res[True]
-    out.update(ms_scan_order=ms0, ms_sorted=ms1, loss_scan_order=loss0, loss_sorted=loss1, logits_rel_diff=rel(l1, l0))
+    (l0, loss0, ms0, mb0), (l1, loss1, ms1, mb1) = res[False], res[True]
+    out.update(ms_scan_order=ms0, ms_sorted=ms1, ms_build_scan_order=mb0, ms_build_sorted=mb1, loss_scan_order=loss0, loss_sorted=loss1,
+               logits_rel_diff=rel(l1, l0))
     if not (abs(loss0 - loss1) < 1e-2 and out["logits_rel_diff"] < 5e-2 and loss1 == loss1):
         out["reason"] = "training step disagrees between the sorted and the scan-order path"
         return out
@@ -126,7 +139,7 @@ def main():
         out["reason"] = f"sorted path not faster ({ms1:.2f} ms vs {ms0:.2f} ms per step)"
         return out
     out["ok"] = True
-    out["reason"] = f"checks passed; {ms0:.2f} -> {ms1:.2f} ms per step (maps + forward + backward on one stream)"
+    out["reason"] = f"checks passed; forward + backward {ms0:.2f} -> {ms1:.2f} ms, map build {mb0:.2f} -> {mb1:.2f} ms (side stream in the bench)"
     return out
 
 

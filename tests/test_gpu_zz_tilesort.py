@@ -19,11 +19,13 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def tile_sort():
     import gcdlss_b200
+    from gcdlss_b200 import config
+    prev = (gcdlss_b200.get_math_mode(), gcdlss_b200.get_tile_sort(), config.tile_sort_min_rows())
     gcdlss_b200.set_math_mode("bf16")
     gcdlss_b200.set_tile_sort(True, min_rows=1)
     yield
-    gcdlss_b200.set_tile_sort(False, min_rows=16384)
-    gcdlss_b200.set_math_mode("fp32")
+    gcdlss_b200.set_tile_sort(prev[1], min_rows=prev[2])
+    gcdlss_b200.set_math_mode(prev[0])
 
 
 def kitti_coords(n_scans=1, n_points=30000):
@@ -109,6 +111,8 @@ def test_fused_blocks_match_the_scan_order_path(cuda):
     bc = torch.from_numpy(kitti_coords(2, 20000)).cuda()
     f = torch.rand(bc.shape[0], 1).cuda()
     labels = torch.randint(0, 17, (bc.shape[0],)).cuda()
+    from gcdlss_b200 import config
+    prev = (gcdlss_b200.get_math_mode(), gcdlss_b200.get_tile_sort(), config.tile_sort_min_rows())
     gcdlss_b200.set_math_mode("bf16")
     results = []
     try:
@@ -122,8 +126,8 @@ def test_fused_blocks_match_the_scan_order_path(cuda):
             grads = torch.cat([p.grad.reshape(-1).float() for p in model.parameters()])
             results.append((out.detach().float(), float(loss), grads))
     finally:
-        gcdlss_b200.set_tile_sort(False, min_rows=16384)
-        gcdlss_b200.set_math_mode("fp32")
+        gcdlss_b200.set_tile_sort(prev[1], min_rows=prev[2])
+        gcdlss_b200.set_math_mode(prev[0])
     (o0, l0, g0), (o1, l1, g1) = results
     cos = float(torch.nn.functional.cosine_similarity(g0, g1, dim=0))
     print(f"logits rel diff {rel_err(o1, o0):.2e}, loss {l0:.5f} vs {l1:.5f}, gradient cosine {cos:.4f}")

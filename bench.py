@@ -107,7 +107,9 @@ def tile_sort_selfcheck(local_rank, scans_per_gpu, kind, n_classes):
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if not lines:
             return {"ok": False, "reason": f"self-check printed no verdict (exit code {r.returncode}): {r.stderr[-300:]}"}
-        return json.loads(lines[-1])
+        verdict = json.loads(lines[-1])
+        # keep the bench's own JSON line strict: no NaN / Infinity tokens
+        return {k: (None if isinstance(v, float) and not np.isfinite(v) else v) for k, v in verdict.items()}
     except Exception as e:  # noqa: BLE001
         return {"ok": False, "reason": f"self-check did not finish: {type(e).__name__}: {e}"}
 

@@ -45,3 +45,14 @@ def test_selfcheck_script_always_prints_a_verdict():
     import torch
     if not torch.cuda.is_available():
         assert verdict["ok"] is False and verdict["reason"]
+
+
+def test_selfcheck_key_bits_match_the_device_code():
+    # the self-check's torch reference of the sort key must use the bit order of csrc/tilesort.cuh
+    import importlib.util
+    from test_tile_sort_model import bit_order
+    spec = importlib.util.spec_from_file_location("selfcheck_tilesort", os.path.join(ROOT, "tools", "selfcheck_tilesort.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.presence_bits(27).tolist() == list(bit_order())
+    assert mod.presence_bits(8).tolist() == list(range(8))

@@ -29,6 +29,19 @@ def rel(a, b):
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
 
 
+def presence_bits(kv):
+    """Bit of each kernel offset in the sort key (csrc/tilesort.cuh): 3x3x3 offsets ranked by (number of non-zero
+    components, k) -- centre lowest, corners on top; 2x2x2: bit k."""
+    if kv != 27:
+        return torch.arange(kv)
+    k = torch.arange(27)
+    cls = ((k % 3) != 1).long() + (((k // 3) % 3) != 1).long() + ((k // 9) != 1).long()
+    order = torch.argsort(cls * 27 + k)
+    bits = torch.empty(27, dtype=torch.long)
+    bits[order] = torch.arange(27)
+    return bits
+
+
 def main():
     device = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     scans = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -51,18 +64,11 @@ def main():
     # ---- 1. the sort itself
     gcdlss_b200.set_tile_sort(False)
     mgr = ME.SparseTensor(features=f, coordinates=bc).coordinate_manager
-    bits27 = None
     for key in ((1, 3, 1, False), (2, 3, 1, False), (1, 2, 2, False), (2, 2, 2, True)):
         km = mgr.kernel_map(*key)
         nbr = km.nbr
         kv = nbr.shape[0]
-        if kv == 27 and bits27 is None:      # offsets ranked by (number of non-zero components, k): centre lowest, corners on top
-            k = torch.arange(27)
-            cls = ((k % 3) != 1).long() + (((k // 3) % 3) != 1).long() + ((k // 9) != 1).long()
-            order = torch.argsort(cls * 27 + k)
-            bits27 = torch.empty(27, dtype=torch.long)
-            bits27[order] = torch.arange(27)
-        bits = (bits27 if kv == 27 else torch.arange(8)).to(dev)
+        bits = presence_bits(kv).to(dev)
         keys = ((nbr >= 0).long() << bits[:, None]).sum(0)
         ref_rows = torch.argsort(keys, stable=True)
         got, rows = ops.kmap_tile_sort(nbr)

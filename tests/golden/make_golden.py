@@ -145,6 +145,31 @@ def part2_oracle():
     print("oracle_frozen.npz:", len(out), "arrays")
 
 
+def part3_tile_sort():
+    """Frozen permutations of the tile sort (csrc/tilesort.cuh) for the tables of oracle_frozen.npz: columns ordered, stably,
+    by the presence mask with offsets ranked (number of non-zero components, k) for 3x3x3 and bit k for 2x2x2.
+    Plain numpy, written out here independently of the test helpers."""
+    frozen = np.load(os.path.join(HERE, "oracle_frozen.npz"))
+    offs = ocd.kernel_offsets(3)
+    rank = np.lexsort((np.arange(27), (offs != 0).sum(1)))
+    bit27 = np.empty(27, np.uint64)
+    bit27[rank] = np.arange(27, dtype=np.uint64)
+    out = {}
+    for name, table, bits in (("subm3_0", frozen["map_subm3_0"], bit27), ("subm3_1", frozen["map_subm3_1"], bit27),
+                              ("down_0", ocd.kmap_down2(frozen["map_parent0"], frozen["map_code0"], frozen["map_coords1"].shape[0]),
+                               np.arange(8, dtype=np.uint64)),
+                              ("up_0", ocd.kmap_up2(frozen["map_parent0"], frozen["map_code0"]), np.arange(8, dtype=np.uint64))):
+        keys = ((table >= 0).astype(np.uint64) << bits[None, :]).sum(1)
+        out[f"rows_{name}"] = np.argsort(keys, kind="stable").astype(np.int32)
+        out[f"keys_{name}"] = keys
+    np.savez_compressed(os.path.join(HERE, "tile_sort_frozen.npz"), **out)
+    print("tile_sort_frozen.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    part1_reference()
-    part2_oracle()
+    if sys.argv[1:] == ["tile_sort"]:           # derived from oracle_frozen.npz alone: does not need the reference checkout
+        part3_tile_sort()
+    else:
+        part1_reference()
+        part2_oracle()
+        part3_tile_sort()

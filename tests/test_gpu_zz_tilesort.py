@@ -57,6 +57,19 @@ def test_sort_of_stride2_tables_equals_numpy(cuda):
         np.testing.assert_array_equal(got.cpu().numpy(), ref)
 
 
+def test_sort_against_the_frozen_permutations(cuda, oracle_frozen):
+    import os
+    from conftest import GOLDEN
+    from gcdlss_b200 import ops
+    from test_tile_sort_model import frozen_tables
+    frozen = np.load(os.path.join(GOLDEN, "tile_sort_frozen.npz"))
+    for name, table in frozen_tables(oracle_frozen).items():
+        table = np.ascontiguousarray(table, np.int32)
+        got, rows = ops.kmap_tile_sort(torch.from_numpy(table).cuda())
+        np.testing.assert_array_equal(rows.cpu().numpy(), frozen[f"rows_{name}"])
+        np.testing.assert_array_equal(got.cpu().numpy(), table[:, frozen[f"rows_{name}"]])
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 32), (96, 96), (256, 128)])
 def test_conv_forward_and_dgrad_with_sorted_table(cuda, tile_sort, cin, cout):
     from gcdlss_b200 import ops

@@ -188,3 +188,21 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
         assert km_1x1.tc_table() == (None, None) and km_1x1.tc_back_table() == (None, None)
     finally:
         gcdlss_b200.set_tile_sort(False, min_rows=16384)
+
+
+def frozen_tables(oracle_frozen):
+    """name -> [kv, n] table of the frozen fixture (tests/golden/make_golden.py part 3)."""
+    n1 = oracle_frozen["map_coords1"].shape[0]
+    return {"subm3_0": oracle_frozen["map_subm3_0"].T, "subm3_1": oracle_frozen["map_subm3_1"].T,
+            "down_0": ocd.kmap_down2(oracle_frozen["map_parent0"], oracle_frozen["map_code0"], n1).T,
+            "up_0": ocd.kmap_up2(oracle_frozen["map_parent0"], oracle_frozen["map_code0"]).T}
+
+
+def test_emulated_sort_against_the_frozen_permutations(emu, oracle_frozen):
+    frozen = np.load(os.path.join(ROOT, "tests", "golden", "tile_sort_frozen.npz"))
+    for name, table in frozen_tables(oracle_frozen).items():
+        table = np.ascontiguousarray(table, np.int32)
+        got, rows, keys = emu_sort(emu, table)
+        np.testing.assert_array_equal(rows, frozen[f"rows_{name}"])
+        np.testing.assert_array_equal(keys, frozen[f"keys_{name}"][frozen[f"rows_{name}"]])
+        np.testing.assert_array_equal(got, table[:, frozen[f"rows_{name}"]])

@@ -143,8 +143,9 @@ def test_what_the_sort_buys_on_synthetic_sweeps(emu):
 def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
     # host logic of coords.KernelMap.tc_table / tc_back_table (no GPU: the sort itself is the emulated one)
     import gcdlss_b200
-    from gcdlss_b200 import coords, ops
+    from gcdlss_b200 import config, coords, ops
 
+    prev = (gcdlss_b200.get_tile_sort(), config.tile_sort_min_rows())
     calls = []
 
     def fake_sort(nbr):
@@ -187,7 +188,7 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
         assert km5.tc_table() == (km5.nbr, None)                            # the 5x5x5 stem goes through im2col: not sorted
         assert km_1x1.tc_table() == (None, None) and km_1x1.tc_back_table() == (None, None)
     finally:
-        gcdlss_b200.set_tile_sort(False, min_rows=16384)
+        gcdlss_b200.set_tile_sort(prev[0], min_rows=prev[1])
 
 
 def frozen_tables(oracle_frozen):

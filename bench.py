@@ -97,23 +97,6 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def tile_sort_selfcheck(local_rank, scans_per_gpu, kind, n_classes):
-    """Runs tools/selfcheck_tilesort.py in a subprocess on this rank's GPU (parity of the tile-sorted convolution path
-    against fp64 and against the scan-order path, and whether it is faster here); returns its JSON verdict.  Whatever goes
-    wrong -- a failed check, a device fault, a hang -- happens in the child and reads as "leave it off"."""
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "selfcheck_tilesort.py"), str(local_rank), str(scans_per_gpu), kind, str(n_classes)]
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)     # well inside the 180 s NCCL timeout of the ranks waiting for the verdict
-        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-        if not lines:
-            return {"ok": False, "reason": f"self-check printed no verdict (exit code {r.returncode}): {r.stderr[-300:]}"}
-        verdict = json.loads(lines[-1])
-        # keep the bench's own JSON line strict: no NaN / Infinity tokens
-        return {k: (None if isinstance(v, float) and not np.isfinite(v) else v) for k, v in verdict.items()}
-    except Exception as e:  # noqa: BLE001
-        return {"ok": False, "reason": f"self-check did not finish: {type(e).__name__}: {e}"}
-
-
 # ------------------------------------------------------------------------------------------ data
 def make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches):
     """Pinned host point clouds [N, 4] (x, y, z, remission) + per-point labels, ``n_batches`` distinct batches."""
@@ -122,7 +105,7 @@ def make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches)
     for b in range(n_batches):
         scans = []
         for s in range(scans_per_gpu):
-            idx = (rank * n_batches + b) * scans_per_gpu + s
+            idx = scan_index(rank, b, s, n_batches, scans_per_gpu)
             xyz, feat = synth.make_scan(kind, idx, n_points=n_points)
             pts = torch.from_numpy(np.concatenate([xyz, feat], 1)).pin_memory()
             lab = torch.from_numpy(np.random.default_rng(idx).integers(0, n_classes, xyz.shape[0])).pin_memory()
@@ -146,62 +129,74 @@ def quantize_batch_on_gpu(scans, q, dev):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def oracle_scan_step(kind, index, n_points, n_classes, params, arch):
+# Nothing below imports the product package (no gcdlss_b200, no models, no MinkowskiEngine shim, no .so): the scan
+# generator is loaded from its file (it needs numpy only) and the parameters come from the oracle's own table of the
+# architecture (oracle/minkunet.py:random_params).
+def load_synth():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gcdlss_synth", os.path.join(_paths.PKG_DIR, "gcdlss_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def scan_index(rank, batch, slot, n_batches, scans_per_gpu):
+    """Index (= generator seed offset) of scan ``slot`` of batch ``batch`` on rank ``rank``: both arms use this."""
+    return (rank * n_batches + batch) * scans_per_gpu + slot
+
+
+def oracle_scan_step(synth, kind, index, n_points, n_classes, params, arch):
     """One scan through the CPU restatement: quantise (numpy) + MinkUNet fwd + CE + bwd (torch CPU)."""
-    from gcdlss_b200 import synth
     from oracle import quantize as oq
     from oracle.minkunet import OracleMinkUNet
     xyz, feat = synth.make_scan(kind, index, n_points=n_points)
     c, um, _ = oq.sparse_quantize_me(xyz, synth.voxel_size(kind))
     bc = oq.batched_coordinates([c])
-    labels = torch.from_numpy(np.random.default_rng(index).integers(0, n_classes, bc.shape[0]))
+    labels = torch.from_numpy(np.random.default_rng(index).integers(0, n_classes, xyz.shape[0])[um])
     for p in params.values():
         if p.is_floating_point() and p.requires_grad:
             p.grad = None
     logits, _, _ = OracleMinkUNet(params, arch, training=True).forward(bc, torch.from_numpy(feat[um]))
     loss = torch.nn.functional.cross_entropy(logits, labels)
     loss.backward()
-    return float(loss)
+    return float(loss), bc.shape[0]
 
 
-def oracle_params(n_classes):
-    from models import minkunet as mu
-    torch.manual_seed(1234)
-    model = mu.MinkUNet34C(1, n_classes)
-    params = {}
-    for k, v in model.state_dict().items():
-        params[k] = v.clone()
-        if v.is_floating_point() and "running" not in k:
-            params[k].requires_grad_(True)
-    return params
-
-
-def time_reference(kind, n_points, n_classes, steps, warmup):
+def time_reference(kind, n_points, n_classes, steps, warmup, scans_per_gpu=4, n_batches=3):
+    """Times the CPU oracle on the first scans of the GPU arm's batch rotation (rank 0: batch 0 slot 0, 1, ...), one scan
+    per step.  Returns (scans/s, seconds per scan, threads, voxels per scan)."""
+    from oracle.minkunet import random_params
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = oracle_params(n_classes)
+    synth = load_synth()
+    params = random_params("MinkUNet34C", 1, n_classes, seed=1234)
+    order = [scan_index(0, b, s, n_batches, scans_per_gpu) for b in range(n_batches) for s in range(scans_per_gpu)]
     for i in range(warmup):
-        oracle_scan_step(kind, i, n_points, n_classes, params, "MinkUNet34C")
+        oracle_scan_step(synth, kind, order[-1 - i], n_points, n_classes, params, "MinkUNet34C")
     t0 = time.perf_counter()
+    vox = 0
     for i in range(steps):
-        oracle_scan_step(kind, 100 + i, n_points, n_classes, params, "MinkUNet34C")
+        vox += oracle_scan_step(synth, kind, order[i % len(order)], n_points, n_classes, params, "MinkUNet34C")[1]
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return 1.0 / dt, dt, cores
+    return 1.0 / dt, dt, cores, vox / max(steps, 1)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kind, scans, n_points, n_classes = WORKLOADS[args.workload]
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    sps, dt, cores = time_reference(kind, n_points, n_classes, steps, warmup)
-    sample = f"{steps} steps of 1 {kind}-like scan each (quantise + MinkUNet34C fwd + CE + bwd), torch CPU fp32, {cores} threads"
+    kind, scans, n_points, n_classes = WORKLOADS[args.workload][:4]
+    steps, warmup = min(args.steps, 4), min(args.warmup, 1)
+    sps, dt, cores, vox = time_reference(kind, n_points, n_classes, steps, warmup, scans)
+    sample = (f"{steps} steps of 1 {kind}-like scan each (the first {steps} scans of the GPU arm's rotation; quantise + MinkUNet34C fwd + CE + bwd), "
+              f"torch CPU fp32, {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "scans/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "CPU restatement of the reference path (MinkowskiEngine itself is not installable here)"},
+            "config": {"workload": args.workload, "voxels_per_scan": vox, "voxels_per_s": sps * vox,
+                       "note": "CPU restatement of the reference path (MinkowskiEngine itself is not installable here); one scan per step"},
             "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "product_modules_imported": sorted(m for m in sys.modules if m.split(".")[0] in ("gcdlss_b200", "MinkowskiEngine", "models"))}
     print(json.dumps(line), flush=True)
 
 
@@ -228,24 +223,15 @@ def run_ours(args):
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     gcdlss_b200.set_math_mode("bf16" if args.dtype == "bf16" else "fp32")
-    kind, scans_per_gpu, n_points, n_classes = WORKLOADS[args.workload]
+    kind, scans_per_gpu, n_points, n_classes = WORKLOADS[args.workload][:4]
     q = synth.voxel_size(kind)
     peaks = load_peaks()
 
-    # Tile-sorted neighbour tables were written after round 1's GPU time had run out, so the library
-    # default is off; the bench switches them on only after a self-check in a child process has passed on this GPU (parity
-    # vs fp64 and vs the scan-order path, and a faster step).  GCDLSS_TILE_SORT=0/1 overrides the check.
-    if os.environ.get("GCDLSS_TILE_SORT") is not None:
-        tile_sort = {"enabled": gcdlss_b200.get_tile_sort(), "how": "GCDLSS_TILE_SORT"}
-    elif args.dtype != "bf16":
-        tile_sort = {"enabled": False, "how": "fp32 path"}
-    else:
-        verdict = tile_sort_selfcheck(local_rank, scans_per_gpu, kind, n_classes)
-        ok = torch.tensor([1 if verdict.get("ok") else 0], device=dev)
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank takes the same path
-        tile_sort = {"enabled": bool(ok.item()), "how": "self-check (tools/selfcheck_tilesort.py)", "verdict": verdict}
-        gcdlss_b200.set_tile_sort(tile_sort["enabled"])
+    # Every rank and every N runs the library's default path (gcdlss_b200.config; GCDLSS_* environment variables override it
+    # for A/B runs) and prints it: no run-time self-check, no timing race deciding the code path.
+    from gcdlss_b200 import config as gcfg
+    path_cfg = {"tile_sort": {"enabled": bool(gcfg.get_tile_sort() and args.dtype == "bf16"), "min_rows": gcfg.tile_sort_min_rows()},
+                "kmap_search": gcfg.get_kmap_search()}
 
     torch.manual_seed(1234)
     model = MinkUNetBase(num_classes=n_classes).to(dev).train()
@@ -483,7 +469,7 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_timed = 3                                   # bounded sample: ~10 s of CPU work on the box's host cores
-        sps, dt, cores = time_reference(kind, n_points, n_classes, n_timed, 1)
+        sps, dt, cores, _ = time_reference(kind, n_points, n_classes, n_timed, 1, scans_per_gpu, n_batches)
         cpu_baseline = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
                         "sample": f"1 warm-up + {n_timed} timed {kind}-like scans, one per step (quantise + MinkUNet34C fwd + CE + bwd) through the CPU oracle, torch CPU fp32, {cores} threads"}
 
@@ -495,7 +481,7 @@ def run_ours(args):
                            "model": "MinkUNet34RC backbone + final head (Stage-1 MinkUNetBase)", "classes": n_classes,
                            "step": "hash + kernel maps (side stream, one batch ahead) + fwd + CE + bwd + grad all-reduce + SGD", "parallelism": f"dp{world}",
                            "l2": f"{n_batches} distinct batches rotate; per-step activations + maps exceed the 126 MB L2",
-                           "tile_sort": tile_sort},
+                           **path_cfg},
                 "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + 8 * scans_per_gpu,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,

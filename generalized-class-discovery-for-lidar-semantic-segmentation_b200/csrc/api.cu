@@ -1,5 +1,7 @@
 // api.cu — error plumbing and library identification.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace gcd {
@@ -15,7 +17,34 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
   set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
   return GCD_ERR_CUDA;
 }
+
+// ---- options: one atomic per key; the environment is read exactly once (thread-safe function-local static)
+namespace {
+struct Options {
+  std::atomic<int32_t> v[GCD_OPT_COUNT_];
+  Options() {
+    static const struct { const char* env; int32_t dflt; } kInit[GCD_OPT_COUNT_] = {
+        {"GCD_PAIRS_FUSED", 1}, {"GCD_GATHER_FLAT", 1}, {"GCD_TC_STAGES", 0}, {"GCD_TC_GROUP", 0}, {"GCD_WG_CHUNK_MIN", 0}};
+    for (int i = 0; i < GCD_OPT_COUNT_; ++i) {
+      const char* e = getenv(kInit[i].env);
+      v[i].store(e ? atoi(e) : kInit[i].dflt, std::memory_order_relaxed);
+    }
+  }
+};
+Options& options() { static Options o; return o; }
+}  // namespace
+int32_t option(int32_t key) { return options().v[key].load(std::memory_order_relaxed); }
 }  // namespace gcd
+
+extern "C" int32_t gcd_set_option(int32_t option, int32_t value) {
+  GCD_REQUIRE(option >= 0 && option < GCD_OPT_COUNT_, "gcd_set_option: unknown option %d", option);
+  gcd::options().v[option].store(value, std::memory_order_relaxed);
+  return GCD_OK;
+}
+extern "C" int32_t gcd_get_option(int32_t option) {
+  if (option < 0 || option >= GCD_OPT_COUNT_) return 0;
+  return gcd::option(option);
+}
 
 extern "C" const char* gcd_last_error_string(void) { return gcd::g_err; }
 extern "C" int32_t gcd_abi_version(void) { return 1; }

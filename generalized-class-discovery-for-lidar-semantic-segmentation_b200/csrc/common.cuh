@@ -27,6 +27,9 @@ int32_t cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::gcd::cuda_fail(e__, what); \
   } while (0)
 
+// process-wide tuning options (api.cu): atomics, initialised once from the environment
+int32_t option(int32_t key);
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

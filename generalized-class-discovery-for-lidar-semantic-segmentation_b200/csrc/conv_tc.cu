@@ -22,6 +22,7 @@
 // History and measurements (what each of these choices bought, and what did not work): DESIGN.md section 4.1,
 // profiles/README.md, tools/ubench/README.md.
 #include <stdlib.h>
+#include <mutex>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -638,6 +639,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
 }
 }  // namespace
 
+// Opt every tcgen05 kernel instantiation into the large dynamic shared memory, once per process (std::call_once: the
+// autograd thread and a prefetch thread may both make the first call).
+static cudaError_t tc_kernels_opt_in();
+
 bool conv_wgrad_tc_supported(const gcd_wgrad_args* a) {
   return a->in_dtype == GCD_BF16 && a->gout_dtype == GCD_BF16 && a->c_in % 16 == 0 && a->c_out % 16 == 0 && a->c_in >= 16 &&
          a->c_out >= 16 && a->c_out <= 256 && a->kv < kWgMaxOffsets && a->ld_in % 8 == 0 && a->ld_gout % 8 == 0 &&
@@ -659,7 +664,7 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   // wide outputs: each work item ends with a 128 x Cout reduction into dW, fewer and longer items keep that traffic down
   // (measured, tools/diag_tc.py: 128->128 at stride 8 23.5 -> 19.5 us, 384->256 58 -> 48 us; narrow layers prefer 512)
   int64_t chunk_min = a->c_out >= 128 ? 1024 : 512;
-  if (const char* e = getenv("GCD_WG_CHUNK_MIN")) chunk_min = std::max(64, atoi(e));      // tuning aid
+  if (const int o = option(GCD_OPT_WG_CHUNK_MIN); o > 0) chunk_min = std::max(64, o);      // tuning aid
   chunk = std::max<int64_t>(chunk_min, std::min<int64_t>(8192, ceil_div(chunk, kWgPairs) * kWgPairs));
   p.chunk = (int)chunk;
   const int stage_bytes = (2 + p.g_slabs) * kSlabBytes;
@@ -669,14 +674,7 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 1024;
   using Kernel = void (*)(const WgParams);
   static const Kernel kernels[4] = {conv_wgrad_tc_kernel<1>, conv_wgrad_tc_kernel<2>, conv_wgrad_tc_kernel<3>, conv_wgrad_tc_kernel<4>};
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (Kernel k : kernels) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_wgrad_tc_kernel)");
-    }
-    attr_set = true;
-  }
+  if (const cudaError_t e = tc_kernels_opt_in(); e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcgen05 kernels)");
   const int64_t work_bound = (ceil_div(a->n_pairs, chunk) + a->kv) * p.m_tiles;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(work_bound, kNumSMs));
   kernels[p.g_slabs - 1]<<<grid, kTcThreads, smem, st>>>(p);
@@ -708,6 +706,26 @@ FwdKernel pick_fwd_kernel(int nq) {
   }
 }
 
+static cudaError_t tc_kernels_opt_in() {
+  static std::once_flag once;
+  static cudaError_t result = cudaSuccess;
+  std::call_once(once, [] {
+    auto opt_in = [](const void* k) {
+      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+      if (e != cudaSuccess && result == cudaSuccess) result = e;
+    };
+    for (int nq : {0, 1, 2, 3, 4, 6}) {
+      opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<false>(nq)));
+      opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<true>(nq)));
+    }
+    opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<1>));
+    opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<2>));
+    opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<3>));
+    opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<4>));
+  });
+  return result;
+}
+
 int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   FwdParams p;
   p.in = (const __nv_bfloat16*)a->in; p.ld_in = a->ld_in; p.nbr = a->nbr; p.kv = a->kv; p.n_out = a->n_out;
@@ -730,11 +748,11 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
   int stages = (kSmemBudget - 1024 - 2 * kMaxKV * kTileM * 4 - 512) / stage_bytes;
   stages = std::min(stages, kMaxStages);
-  if (const char* e = getenv("GCD_TC_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));   // tuning aid
+  if (const int o = option(GCD_OPT_TC_STAGES); o > 0) stages = std::max(2, std::min(stages, o));   // tuning aid
   if (stages < 2) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
   p.group = stages <= 4 ? 2 : 1;      // measured: one warp per stage is best with >= 5 stages, a warp pair when the stages are few and fat
-  if (const char* e = getenv("GCD_TC_GROUP")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) p.group = g; }   // tuning aid
+  if (const int g = option(GCD_OPT_TC_GROUP); g == 1 || g == 2 || g == 4 || g == 8) p.group = g;   // tuning aid
 #ifdef GCD_TC_PROFILE
   p.dbg = g_debug_buffer;
   p.ablate = getenv("GCD_TC_ABLATE") ? atoi(getenv("GCD_TC_ABLATE")) : 0;
@@ -743,18 +761,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   const size_t smem = L.total + 1024;
   const int nq_sel = (a->c_in + kChunkK - 1) / kChunkK;
   const FwdKernel kernel = p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel);
-  {
-    // opt-in to the large dynamic shared memory once per kernel instantiation (benign race: the call is idempotent)
-    static FwdKernel done[32];
-    static int n_done = 0;
-    bool seen = false;
-    for (int i = 0; i < n_done; ++i) seen = seen || done[i] == kernel;
-    if (!seen) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_fwd_tc_kernel)");
-      if (n_done < 32) done[n_done++] = kernel;
-    }
-  }
+  if (const cudaError_t e = tc_kernels_opt_in(); e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcgen05 kernels)");
   if (a->c_in > 8 * kChunkK) { set_error("conv_forward_tc: more than 512 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;
   const unsigned grid = (unsigned)std::min<int64_t>(n_work, kNumSMs);

@@ -428,8 +428,7 @@ extern "C" int32_t gcd_pairs_from_table(const int32_t* nbr, int64_t n_out, int32
   int32_t* flags = (int32_t*)p; p += align_up((size_t)total * 4, 256);
   int32_t* pos = (int32_t*)p;   p += align_up((size_t)total * 4, 256);
   int32_t* tot = (int32_t*)p;   p += align_up(4, 256);
-  static const bool fused = getenv("GCD_PAIRS_FUSED") && atoi(getenv("GCD_PAIRS_FUSED")) != 0;   // opt-in until run on a B200
-  if (fused) return pairs_from_table_fused(nbr, n_out, kv, pair_in, pair_out, pair_off, tot, p, scan_workspace_bytes(total), st);
+  if (option(GCD_OPT_PAIRS_FUSED)) return pairs_from_table_fused(nbr, n_out, kv, pair_in, pair_out, pair_off, tot, p, scan_workspace_bytes(total), st);
   flag_valid_kernel<<<grid_for(total), kThreads, 0, st>>>(nbr, total, flags);
   int32_t rc = exclusive_scan_i32(flags, pos, total, tot, p, scan_workspace_bytes(total), st);
   if (rc != GCD_OK) return rc;

@@ -73,8 +73,7 @@ extern "C" int32_t gcd_rows_gather(const float* in, int64_t ld_in, const int64_t
   if (n_out == 0) return GCD_OK;
   const int vec = (c % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  static const bool flat = getenv("GCD_GATHER_FLAT") && atoi(getenv("GCD_GATHER_FLAT")) != 0;   // opt-in until run on a B200
-  if (vec && flat)
+  if (vec && option(GCD_OPT_GATHER_FLAT))
     rows_gather_flat_kernel<<<(unsigned)ceil_div(n_out * (c / 4), kGatherThreads * kGatherUnroll), kGatherThreads, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(in), ld_in / 4, idx, n_out, c / 4, reinterpret_cast<float4*>(out), ld_out / 4);
   else

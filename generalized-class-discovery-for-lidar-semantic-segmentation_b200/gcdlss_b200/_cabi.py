@@ -18,6 +18,7 @@ F32, BF16 = 0, 1
 MATH_FP32_SIMT, MATH_BF16_TC = 0, 1
 ROUND_FLOOR, ROUND_HALF_EVEN = 0, 1
 DEV_KEY_RANGE, DEV_DUPLICATE, DEV_TABLE_FULL = 1, 2, 4
+OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN = range(5)
 
 
 def build(force: bool = False) -> str:
@@ -110,6 +111,8 @@ PROTOTYPES = {
     "gcd_last_error_string": (C.c_char_p, []),
     "gcd_abi_version": (_i32, []),
     "gcd_has_tcgen05": (_i32, []),
+    "gcd_set_option": (_i32, [_i32, _i32]),
+    "gcd_get_option": (_i32, [_i32]),
     "gcd_quantize_f32": (_i32, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp]),
     "gcd_quantize_f64": (_i32, [_vp, _i64, _i64, _i32, _f64, _i32, _vp, _vp]),
     "gcd_colmin_i32": (_i32, [_vp, _i64, _i32, _vp, _vp]),

@@ -7,8 +7,6 @@ tensor derived from it, so a teacher and a student that consume the same input t
 """
 from __future__ import annotations
 
-import weakref
-
 import torch
 
 from . import config, ops
@@ -24,57 +22,72 @@ class CoordMap:
         self.code = None     # [n] child offset index dx + 2dy + 4dz
 
 
-class KernelMap:
-    """A dense neighbour table plus, lazily, its per-offset pair lists.
+class NeighbourTable:
+    """One dense neighbour table ``nbr [kv, n_out]`` (int32, -1 = none) plus what is derived from it on first use:
+    the tile-sorted copy for the tcgen05 convolution and the per-offset pair lists for wgrad.  A table references
+    nothing but device tensors, so kernel maps can share tables (a stride-2 map's dgrad table is the matching
+    transposed map's forward table) without reference cycles and without going back to the manager."""
+    __slots__ = ("nbr", "kv", "n_out", "_sorted", "_pairs")
 
-    nbr [kv, n_out] int32 feeds the output-stationary forward; ``back_key`` names the kernel map whose
-    table drives the matching dgrad (see include/gcdlss_b200.h, gcd_conv_args).  The manager is held
-    weakly: maps must die by reference counting when the batch's tensors die (a manager <-> map cycle
-    would park hundreds of MB per step until the cyclic GC runs)."""
-
-    def __init__(self, nbr, n_in, n_out, kv, manager, back_key, back_mirror):
-        self.nbr, self.n_in, self.n_out, self.kv = nbr, n_in, n_out, kv
-        self._mgr = weakref.ref(manager)
-        self._back_key, self.back_mirror = back_key, back_mirror
+    def __init__(self, nbr, kv, n_out):
+        self.nbr, self.kv, self.n_out = nbr, kv, n_out
+        self._sorted = None          # (tile-sorted table, its column -> output row permutation)
         self._pairs = None
-        self._sorted = None          # (tile-sorted table, its column -> output row permutation), built on first use
 
     def tc_table(self):
         """(table, out_rows) for the tcgen05 convolution: the tile-sorted copy when tile sorting is on and this is a
-        3x3x3 or 2x2x2 map with enough rows to pay for the sort, else (nbr, None).  Pair lists always come from ``nbr``."""
+        3x3x3 or 2x2x2 table with enough rows to pay for the sort, else (nbr, None)."""
         if self.nbr is None or self.kv not in (8, 27) or not config.get_tile_sort() or self.n_out < config.tile_sort_min_rows():
             return self.nbr, None
         if self._sorted is None:
             self._sorted = ops.kmap_tile_sort(self.nbr)
         return self._sorted
 
+    @property
+    def pairs(self):
+        if self._pairs is None and self.nbr is not None:
+            self._pairs = ops.pairs_from_table(self.nbr)
+        return self._pairs
+
+    def device_tensors(self):
+        out = [self.nbr] if self.nbr is not None else []
+        if self._pairs is not None:
+            out += list(self._pairs)
+        if self._sorted is not None:
+            out += list(self._sorted)
+        return out
+
+
+class KernelMap:
+    """Forward table of a convolution plus the table that drives the matching dgrad (see include/gcdlss_b200.h,
+    gcd_conv_args).  Both are held STRONGLY (as NeighbourTable objects, i.e. device tensors): an autograd node that
+    keeps its KernelMap keeps everything backward will read, whatever happened to the SparseTensors and their
+    coordinate manager in the meantime (a Lightning ``training_step`` returns only the loss,
+    ref modules/exp.py:249-267)."""
+    __slots__ = ("fwd", "back", "n_in", "n_out", "kv", "back_mirror")
+
+    def __init__(self, fwd: NeighbourTable, n_in, n_out, back, back_mirror):
+        self.fwd, self.back = fwd, back
+        self.n_in, self.n_out, self.kv, self.back_mirror = n_in, n_out, fwd.kv, back_mirror
+
+    @property
+    def nbr(self):
+        return self.fwd.nbr
+
+    def tc_table(self):
+        return self.fwd.tc_table()
+
     def tc_back_table(self):
         """The same for the table that drives the matching dgrad."""
-        if self._back_key is None:
-            return None, None
-        if self._back_key == "self":
-            return self.tc_table()
-        mgr = self._mgr()
-        if mgr is None:
-            raise RuntimeError("the coordinate manager of this kernel map no longer exists")
-        return mgr.kernel_map(*self._back_key).tc_table()
+        return self.back.tc_table() if self.back is not None else (None, None)
 
     @property
     def pairs(self):
-        if self._pairs is None:
-            self._pairs = ops.pairs_from_table(self.nbr) if self.nbr is not None else None
-        return self._pairs
+        return self.fwd.pairs
 
     @property
     def back_nbr(self):
-        if self._back_key is None:
-            return None
-        if self._back_key == "self":
-            return self.nbr
-        mgr = self._mgr()
-        if mgr is None:
-            raise RuntimeError("the coordinate manager of this kernel map no longer exists")
-        return mgr.kernel_map(*self._back_key).nbr
+        return self.back.nbr if self.back is not None else None
 
     def num_pairs(self) -> int:
         """Exact pair count (one device read; used for FLOP accounting only)."""
@@ -97,6 +110,7 @@ class CoordinateManager:
         else:
             self.maps = {1: CoordMap(coords, ops.hash_build(coords, self.status), 1)}
         self._kmaps = {}
+        self._tables = {}      # kernel-map key -> NeighbourTable (a stride-2 map and its transpose share theirs)
 
     # -- coordinate maps -------------------------------------------------------------------
     def check(self):
@@ -141,16 +155,18 @@ class CoordinateManager:
             if m.runs is not None:
                 out.append(m.runs.slots)
             out += [t for t in (m.parent, m.code) if t is not None]
-        for km in self._kmaps.values():
-            if km.nbr is not None:
-                out.append(km.nbr)
-            if km._pairs is not None:
-                out += list(km._pairs)
-            if km._sorted is not None:
-                out += list(km._sorted)
+        for table in self._tables.values():
+            out += table.device_tensors()
         return out
 
     # -- kernel maps -----------------------------------------------------------------------
+    def _table(self, key, build) -> NeighbourTable:
+        t = self._tables.get(key)
+        if t is None:
+            nbr, kv, n_out = build()
+            t = self._tables[key] = NeighbourTable(nbr, kv, n_out)
+        return t
+
     def kernel_map(self, ts_in: int, kernel_size: int, stride: int, transposed: bool) -> KernelMap:
         key = (ts_in, kernel_size, stride, transposed)
         km = self._kmaps.get(key)
@@ -158,30 +174,31 @@ class CoordinateManager:
             return km
         if kernel_size == 1 and stride == 1:
             m = self.get_map(ts_in)
-            km = KernelMap(None, m.n, m.n, 1, self, None, False)
+            km = KernelMap(self._table(key, lambda: (None, 1, m.n)), m.n, m.n, None, False)
         elif stride == 1 and kernel_size in (3, 5) and not transposed:
             m = self.get_map(ts_in)
-            if self.runs:
-                if m.runs is None:       # coarse maps: built on first use from the map's unique coordinates
-                    m.runs = ops.runtable_build(m.coords, ts_in, self.status)
-                nbr = ops.kmap_subm_runs(m.coords, m.runs, kernel_size, ts_in)
-            else:
-                nbr = ops.kmap_subm(m.coords, m.table, kernel_size, ts_in)
+
+            def build():
+                if self.runs:
+                    if m.runs is None:       # coarse maps: built on first use from the map's unique coordinates
+                        m.runs = ops.runtable_build(m.coords, ts_in, self.status)
+                    return ops.kmap_subm_runs(m.coords, m.runs, kernel_size, ts_in), kernel_size ** 3, m.n
+                return ops.kmap_subm(m.coords, m.table, kernel_size, ts_in), kernel_size ** 3, m.n
+            t = self._table(key, build)
             # stride-1 symmetric kernel: the transposed map is the same table with mirrored offsets
-            km = KernelMap(nbr, m.n, m.n, kernel_size ** 3, self, "self", True)
-        elif stride == 2 and kernel_size == 2 and not transposed:
-            fine = self.get_map(ts_in)
-            coarse = self.get_map(ts_in * 2)
-            nbr = ops.kmap_down2(fine.parent, fine.code, coarse.n)
-            km = KernelMap(nbr, fine.n, coarse.n, 8, self, (ts_in * 2, 2, 2, True), False)
-        elif stride == 2 and kernel_size == 2 and transposed:
-            if ts_in % 2 or ts_in // 2 not in self.maps:
+            km = KernelMap(t, m.n, m.n, t, True)
+        elif stride == 2 and kernel_size == 2:
+            # A stride-2 map and the transposed map between the same two resolutions are each other's dgrad table;
+            # both tables are built now (three small launches) so that neither map ever needs the manager again.
+            ts_fine = ts_in // 2 if transposed else ts_in
+            if transposed and (ts_in % 2 or ts_fine not in self.maps):
                 raise RuntimeError("transposed convolution needs the finer coordinate map to exist already "
                                    "(MinkUNet decoders only upsample onto encoder maps)")
-            fine = self.get_map(ts_in // 2)
-            coarse = self.get_map(ts_in)
-            nbr = ops.kmap_up2(fine.parent, fine.code)
-            km = KernelMap(nbr, coarse.n, fine.n, 8, self, (ts_in // 2, 2, 2, False), False)
+            fine = self.get_map(ts_fine)
+            coarse = self.get_map(ts_fine * 2)
+            down = self._table((ts_fine, 2, 2, False), lambda: (ops.kmap_down2(fine.parent, fine.code, coarse.n), 8, coarse.n))
+            up = self._table((ts_fine * 2, 2, 2, True), lambda: (ops.kmap_up2(fine.parent, fine.code), 8, fine.n))
+            km = KernelMap(up, coarse.n, fine.n, down, False) if transposed else KernelMap(down, fine.n, coarse.n, up, False)
         else:
             raise NotImplementedError(f"kernel_size={kernel_size}, stride={stride}, transposed={transposed} is not on the "
                                       "MinkUNet path (supported: 1/1, 3/1, 5/1, 2/2 and transposed 2/2)")

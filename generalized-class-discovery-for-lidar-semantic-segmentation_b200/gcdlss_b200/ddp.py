@@ -18,6 +18,12 @@ class GradBucketReducer:
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        if self.world > 1:
+            # like DistributedDataParallel: every rank starts from rank 0's parameters (ranks that constructed the model
+            # under different RNG state would otherwise diverge silently).  Buffers: see broadcast_buffers().
+            with torch.no_grad():
+                for p in self.params:
+                    dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
         self.buckets = []            # (flat tensor, [params])
         self._owner = {}
         self._pending = []
@@ -59,8 +65,26 @@ class GradBucketReducer:
         if self._pending[b] == 0 and self.world > 1:
             self._handles.append(dist.all_reduce(self.buckets[b][0], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def broadcast_buffers(self, module):
+        """Rank 0's buffers (BN running statistics) to every rank; call once after construction."""
+        if self.world > 1:
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            for b in module.buffers():
+                dist.broadcast(b.data, src=src, group=self.group)
+
+    def check_views(self):
+        """``.grad`` of every parameter must still alias its flat bucket (``optimizer.zero_grad(set_to_none=True)`` detaches
+        them silently; use ``reset()`` instead)."""
+        for flat, plist in self.buckets:
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            for p in plist:
+                if p.grad is None or not (lo <= p.grad.data_ptr() < hi):
+                    raise RuntimeError("GradBucketReducer: a parameter's .grad no longer aliases its all-reduce bucket; "
+                                       "zero gradients with reducer.reset(), not optimizer.zero_grad(set_to_none=True)")
+
     def finish(self):
         """Wait for the outstanding all-reduces and turn sums into means."""
+        self.check_views()
         if self.world > 1:
             for b, left in enumerate(self._pending):       # parameters that received no gradient this step
                 if left > 0:
@@ -76,6 +100,8 @@ class GradBucketReducer:
 
 
 def shard_scans(n_scans_global: int, rank: int, world: int):
-    """Indices of the scans rank ``rank`` processes (contiguous blocks, like a DistributedSampler without shuffle)."""
-    per = n_scans_global // world
-    return list(range(rank * per, (rank + 1) * per))
+    """Indices of the scans rank ``rank`` processes (contiguous blocks, like a DistributedSampler without shuffle).
+    The ``n_scans_global % world`` trailing scans go one each to the first ranks, so none is dropped."""
+    per, extra = divmod(n_scans_global, world)
+    start = rank * per + min(rank, extra)
+    return list(range(start, start + per + (1 if rank < extra else 0)))

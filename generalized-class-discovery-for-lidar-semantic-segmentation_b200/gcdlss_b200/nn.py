@@ -148,6 +148,11 @@ class MinkowskiBatchNorm(nn.Module):
         # device scalar when somebody looks, instead of one tiny kernel per layer per step.
         self._pending_batches = 0
         self.register_state_dict_pre_hook(_flush_batches_hook)
+        # a loaded checkpoint replaces the counter: batches counted before the load must not be added onto it
+        self._register_load_state_dict_pre_hook(self._drop_pending_batches)
+
+    def _drop_pending_batches(self, *_args):
+        self._pending_batches = 0
 
     def _flush_batches(self):
         if self._pending_batches:

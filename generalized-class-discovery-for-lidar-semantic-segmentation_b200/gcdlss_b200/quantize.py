@@ -8,11 +8,26 @@
 * ``voxelize_minkunet``: the 'minkunet' branch of ``Voxelizer.voxelize``
   (ref models/voxelizer.py:271-302): round-half-even, min shift, voxels in ascending key order.
 
-Inputs may live on the host (numpy / CPU tensors, as in DataLoader workers); they are copied to
-the GPU, quantised and deduplicated there by the hash kernels, and the maps are returned as CPU
-int64 tensors, which is what the reference's callers index with.
+Inputs may live on the host (numpy / CPU tensors); they are copied to the GPU, quantised and
+deduplicated there by the hash kernels, and the maps are returned as CPU int64 tensors, which is
+what the reference's callers index with.
+
+DataLoader workers.  The reference calls ``ME.utils.sparse_quantize`` from ``Dataset.__getitem__`` inside
+DataLoader workers (ref modules/exp.py:176-202, ``num_workers=8``).  Workers are *forked* by default and
+CUDA cannot be initialised in a forked child of a process that already holds a context; there is no CPU
+implementation to fall back to (by design).  Two supported arrangements:
+
+* ``DataLoader(..., multiprocessing_context="spawn")``: every worker owns a CUDA context and quantises on the
+  GPU; the call works unchanged (tests/test_quantize_workers.py);
+* quantise after the loader, on the training process's GPU: ``sparse_quantize_gpu`` on a side stream through
+  ``prefetch.BatchPrefetcher`` (what bench.py's e2e loop does) -- the faster of the two.
+
+A call from a forked worker raises a RuntimeError that says so instead of torch's "Cannot re-initialize CUDA in
+forked subprocess".
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -21,7 +36,20 @@ from . import ops
 from ._cabi import ROUND_FLOOR, ROUND_HALF_EVEN
 
 
+_IMPORT_PID = os.getpid()
+
+
+_forked = [False]
+if hasattr(os, "register_at_fork"):
+    os.register_at_fork(after_in_child=lambda: _forked.__setitem__(0, True))
+
+
 def _device(device=None):
+    if _forked[0] and getattr(torch.cuda, "_is_in_bad_fork", lambda: False)():
+        raise RuntimeError(
+            "gcdlss_b200.sparse_quantize was called in a fork()ed worker of a process that already initialised CUDA; CUDA cannot be "
+            "used there and there is no CPU fallback.  Use DataLoader(..., multiprocessing_context='spawn'), or return raw points "
+            "from the dataset and quantise on the training GPU (gcdlss_b200.quantize.sparse_quantize_gpu / prefetch.BatchPrefetcher).")
     if device is not None and str(device) != "cpu":
         return torch.device(device)
     if not torch.cuda.is_available():

@@ -10,6 +10,7 @@ import numpy as np
 
 SENSOR_HEIGHT = 1.73
 MAX_RANGE = 80.0
+SENSOR_CLEARANCE = 2.5      # metres of free space around the sensor in x and y
 
 PRESETS = {
     # name: (beams, elevation top/bottom in degrees, azimuth steps, voxel size, feature scale)
@@ -41,6 +42,10 @@ def _cast(dirs, rng, n_boxes=40):
             t = np.minimum(t, np.where(tw > 0, tw, inf))
         centers = np.stack([rng.uniform(-35, 35, n_boxes), rng.uniform(-7.5, 7.5, n_boxes), np.zeros(n_boxes)], 1)
         sizes = np.stack([rng.uniform(1.5, 5.0, n_boxes), rng.uniform(1.2, 2.5, n_boxes), rng.uniform(1.2, 3.0, n_boxes)], 1)
+        # no box on top of the ego vehicle: a box that contains (or hugs) the sensor swallows every ray and leaves a
+        # 2-4 k-voxel "scan"; boxes whose footprint comes within SENSOR_CLEARANCE of the origin are pushed out along x
+        near = (np.abs(centers[:, 0]) < sizes[:, 0] / 2 + SENSOR_CLEARANCE) & (np.abs(centers[:, 1]) < sizes[:, 1] / 2 + SENSOR_CLEARANCE)
+        centers[near, 0] = np.where(centers[near, 0] >= 0, 1.0, -1.0) * (sizes[near, 0] / 2 + SENSOR_CLEARANCE + rng.uniform(0.0, 4.0, int(near.sum())))
         lo = centers - sizes / 2 * np.array([1, 1, 0])
         hi = lo + sizes
         inv = 1.0 / dirs                                                           # slab method, rays x boxes

@@ -73,6 +73,21 @@ int32_t gcd_abi_version(void);
 /* 1 when the library was built with the tcgen05 kernels (always, for sm_100a). */
 int32_t gcd_has_tcgen05(void);
 
+/* Process-wide tuning options.  They select between implementations that produce IDENTICAL results (bit-exact for the
+ * integer kernels); nothing here changes what a call computes.  Values are plain atomics: reads and writes from any
+ * thread are safe, a call in flight sees either the old or the new value.  Initial values come from the environment
+ * variable of the same name (GCD_PAIRS_FUSED, ...) read once, at the first use of the library, then never again. */
+typedef enum {
+  GCD_OPT_PAIRS_FUSED = 0,   /* 1 (default): pair lists straight from the table, two passes; 0: flag / scan / emit */
+  GCD_OPT_GATHER_FLAT = 1,   /* 1 (default): gcd_rows_gather deals float4 elements flat; 0: one warp per row */
+  GCD_OPT_TC_STAGES = 2,     /* > 0: cap on the shared-memory ring depth of the tcgen05 convolution (tuning aid) */
+  GCD_OPT_TC_GROUP = 3,      /* 1 | 2 | 4 | 8: gather warps per ring slot; 0 = chosen per launch (tuning aid) */
+  GCD_OPT_WG_CHUNK_MIN = 4,  /* > 0: minimum pairs per wgrad work item (tuning aid) */
+  GCD_OPT_COUNT_ = 5
+} gcd_option;
+int32_t gcd_set_option(int32_t option, int32_t value);
+int32_t gcd_get_option(int32_t option);
+
 /* ------------------------------------------------------------------ quantisation -------- */
 /* out[i, d] = (int32) round_mode( pts[i*ld + d] / q ), d < dims (dims = 3 or 4).  The division
  * is an IEEE division in the input precision (never a multiply by a reciprocal). */

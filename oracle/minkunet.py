@@ -106,3 +106,55 @@ class OracleMinkUNet:
         """ref models/minkunet.py:349-362: [final | final3 | max(final2)]."""
         y2 = self.head(feats96, "final2").max(dim=1, keepdim=True)[0]
         return torch.cat([self.head(feats96), self.head(feats96, "final3"), y2], 1)
+
+
+def random_params(arch: str = "MinkUNet34C", in_channels: int = 1, n_classes: int = 17, seed: int = 1234, dtype=torch.float32) -> dict:
+    """A random-init ``state_dict`` of ``arch`` under the reference's parameter names, built from the topology alone
+    (ref models/minkunet.py:59-132, models/resnet.py:90-122) so that the CPU baseline never touches the product
+    package.  Kernels are N(0, sqrt(2 / (kernel_volume * Cout)))-distributed (ME.utils.kaiming_normal_ with
+    mode='fan_out', ref models/resnet.py:62-69), BN weight 1 / bias 0; float tensors other than running statistics
+    require grad."""
+    block, layers, planes, init_dim = ARCHS[arch]
+    expansion = 4 if block == "bottleneck" else 1
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+
+    def conv(name, kv, cin, cout, bias=False):
+        shape = (cin, cout) if kv == 1 else (kv, cin, cout)
+        p[name + ".kernel"] = (torch.randn(shape, generator=g, dtype=dtype) * (2.0 / (kv * cout)) ** 0.5).requires_grad_(True)
+        if bias:
+            p[name + ".bias"] = torch.zeros((1, cout), dtype=dtype).requires_grad_(True)
+
+    def bn(name, c):
+        p[name + ".bn.weight"] = torch.ones(c, dtype=dtype).requires_grad_(True)
+        p[name + ".bn.bias"] = torch.zeros(c, dtype=dtype).requires_grad_(True)
+        p[name + ".bn.running_mean"] = torch.zeros(c, dtype=dtype)
+        p[name + ".bn.running_var"] = torch.ones(c, dtype=dtype)
+        p[name + ".bn.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    def stage(name, inplanes, width, n_blocks):
+        for i in range(n_blocks):
+            b = f"{name}.{i}"
+            cin = inplanes if i == 0 else width * expansion
+            if block == "basic":
+                conv(b + ".conv1", 27, cin, width); bn(b + ".norm1", width)
+                conv(b + ".conv2", 27, width, width); bn(b + ".norm2", width)
+            else:
+                conv(b + ".conv1", 1, cin, width); bn(b + ".norm1", width)
+                conv(b + ".conv2", 27, width, width); bn(b + ".norm2", width)
+                conv(b + ".conv3", 1, width, width * expansion); bn(b + ".norm3", width * expansion)
+            if i == 0 and cin != width * expansion:
+                conv(b + ".downsample.0", 1, cin, width * expansion); bn(b + ".downsample.1", width * expansion)
+        return width * expansion
+
+    conv("conv0p1s1", 125, in_channels, init_dim); bn("bn0", init_dim)
+    inplanes, skip_width = init_dim, [init_dim]
+    for i in range(4):
+        conv(DOWN_CONVS[i], 8, inplanes, inplanes); bn(f"bn{i + 1}", inplanes)
+        inplanes = stage(f"block{i + 1}", inplanes, planes[i], layers[i])
+        skip_width.append(inplanes)
+    for i in range(4):
+        conv(UP_CONVS[i], 8, inplanes, planes[i + 4]); bn(f"bntr{i + 4}", planes[i + 4])
+        inplanes = stage(f"block{i + 5}", planes[i + 4] + skip_width[3 - i], planes[i + 4], layers[i + 4])
+    conv("final", 1, inplanes, n_classes, bias=True)
+    return p

@@ -15,10 +15,13 @@ def _worker(rank, world, port, out):
     from gcdlss_b200.ddp import GradBucketReducer, shard_scans
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(0)
+    torch.manual_seed(rank)                       # ranks construct DIFFERENT models: the reducer must broadcast rank 0's
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 3))
     reducer = GradBucketReducer(net.parameters(), bucket_bytes=256)      # several small buckets
     assert len(reducer.buckets) > 1
+    torch.manual_seed(0)
+    rank0_net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 3))
+    assert all(torch.equal(a, b) for a, b in zip(net.parameters(), rank0_net.parameters())), "parameters were not broadcast from rank 0"
     gen = torch.Generator().manual_seed(100)
     data = torch.randn(8, 8, generator=gen)
     mine = shard_scans(8, rank, world)
@@ -37,6 +40,14 @@ def _worker(rank, world, port, out):
         g = torch.cat([p.grad.flatten() for p in ref_net.parameters()])
         acc = g if acc is None else acc + g
     ok = torch.allclose(grads, acc / world, rtol=1e-5, atol=1e-6)
+    # zero_grad(set_to_none=True) detaches .grad from the buckets: finish() must say so instead of reducing stale zeros
+    net.zero_grad(set_to_none=True)
+    net(data[mine]).pow(2).sum().backward()
+    try:
+        reducer.check_views()
+        ok = False
+    except RuntimeError:
+        pass
     if rank == 0:
         open(out, "w").write("ok" if ok else "mismatch")
     dist.destroy_process_group()
@@ -54,3 +65,5 @@ def test_shard_scans_partition():
     for world in (1, 2, 4, 8):
         allidx = sum((shard_scans(16, r, world) for r in range(world)), [])
         assert sorted(allidx) == list(range(16))
+    assert [len(shard_scans(10, r, 4)) for r in range(4)] == [3, 3, 2, 2]                      # no trailing scan is dropped
+    assert sorted(sum((shard_scans(10, r, 4) for r in range(4)), [])) == list(range(10))

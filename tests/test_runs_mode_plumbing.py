@@ -36,6 +36,9 @@ def runs_manager(emu, monkeypatch):  # noqa: F811
         coarse, parent, code = ocd.stride2(c.numpy(), ts)
         return torch.from_numpy(coarse), torch.from_numpy(parent), torch.from_numpy(code), None      # no point-wise coarse table needed
 
+    as_cols = lambda t: torch.from_numpy(np.ascontiguousarray(t.T))
+    monkeypatch.setattr(ops, "kmap_down2", lambda parent, code, n_coarse: as_cols(ocd.kmap_down2(parent.numpy(), code.numpy(), n_coarse)))
+    monkeypatch.setattr(ops, "kmap_up2", lambda parent, code: as_cols(ocd.kmap_up2(parent.numpy(), code.numpy())))
     monkeypatch.setattr(ops, "new_batch", lambda: None)
     monkeypatch.setattr(ops, "runtable_build", runtable_build)
     monkeypatch.setattr(ops, "kmap_subm_runs", kmap_subm_runs)
@@ -70,3 +73,27 @@ def test_duplicates_are_reported(runs_manager):
     c = torch.tensor([[0, 1, 2, 3], [0, 4, 4, 4], [0, 1, 2, 3]], dtype=torch.int32)
     with pytest.raises(RuntimeError, match="duplicate"):
         CoordinateManager(c).check()
+
+
+def test_kernel_maps_outlive_their_manager(runs_manager):
+    """A Lightning training_step returns only the loss (ref modules/exp.py:249-267): by the time backward runs the
+    SparseTensors and their coordinate manager are gone.  Every map must carry its own dgrad table."""
+    import gc
+    import weakref
+    CoordinateManager, _ = runs_manager
+    bc = small_cloud(43, 2500, spread=0.5, batch=0)
+    lv = ocd.CoordLevels(bc)
+    mgr = CoordinateManager(torch.from_numpy(bc))
+    km3 = mgr.kernel_map(1, 3, 1, False)
+    km_down = mgr.kernel_map(1, 2, 2, False)       # asked for alone: an encoder-only network never builds the transposed map
+    km_1x1 = mgr.kernel_map(2, 1, 1, False)
+    ref = weakref.ref(mgr)
+    del mgr
+    gc.collect()
+    assert ref() is None, "kernel maps must not keep the manager alive (no map <-> manager cycle)"
+    assert km3.back_nbr is km3.nbr and km3.tc_back_table()[0] is km3.nbr
+    parent, code = lv.parent[0], lv.code[0]
+    np.testing.assert_array_equal(km_down.nbr.numpy().T, ocd.kmap_down2(parent, code, lv.coords[1].shape[0]))
+    np.testing.assert_array_equal(km_down.back_nbr.numpy().T, ocd.kmap_up2(parent, code))
+    assert km_down.tc_back_table()[0] is km_down.back_nbr
+    assert km_1x1.back_nbr is None and km_1x1.tc_back_table() == (None, None)

@@ -155,22 +155,16 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
 
     monkeypatch.setattr(ops, "kmap_tile_sort", fake_sort)
 
-    class Manager:                      # stands in for the CoordinateManager (held weakly by its maps)
-        def __init__(self):
-            self.maps = {}
-
-        def kernel_map(self, *key):
-            return self.maps[key]
-
     c = small_cloud(5, 800, spread=0.3, batch=0)
     nbr = torch.from_numpy(np.ascontiguousarray(ocd.kmap_subm(c, 3, 1).T))
     n = nbr.shape[1]
-    mgr = Manager()
-    km3 = coords.KernelMap(nbr, n, n, 27, mgr, "self", True)
-    km_down = coords.KernelMap(torch.zeros((8, 10), dtype=torch.int32), n, 10, 8, mgr, (2, 2, 2, True), False)
-    km_up = coords.KernelMap(torch.zeros((8, n), dtype=torch.int32), 10, n, 8, mgr, (1, 2, 2, False), False)
-    km_1x1 = coords.KernelMap(None, n, n, 1, mgr, None, False)
-    mgr.maps = {(2, 2, 2, True): km_up, (1, 2, 2, False): km_down}
+    t3 = coords.NeighbourTable(nbr, 27, n)
+    t_dn = coords.NeighbourTable(torch.zeros((8, 10), dtype=torch.int32), 8, 10)
+    t_up = coords.NeighbourTable(torch.zeros((8, n), dtype=torch.int32), 8, n)
+    km3 = coords.KernelMap(t3, n, n, t3, True)
+    km_down = coords.KernelMap(t_dn, n, 10, t_up, False)        # a stride-2 map and its transpose share their tables
+    km_up = coords.KernelMap(t_up, 10, n, t_dn, False)
+    km_1x1 = coords.KernelMap(coords.NeighbourTable(None, 1, n), n, n, None, False)
     try:
         gcdlss_b200.set_tile_sort(False)
         assert km3.tc_table() == (km3.nbr, None) and not calls
@@ -184,7 +178,8 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
         t_down, r_down = km_down.tc_table()                                 # 2x2x2 tables are sorted as well
         assert r_down is not None and torch.equal(t_down, km_down.nbr[:, r_down.long()])
         assert km_up.tc_back_table()[0] is t_down and km_down.tc_back_table()[0] is km_up.tc_table()[0]
-        km5 = coords.KernelMap(torch.zeros((125, n), dtype=torch.int32), n, n, 125, mgr, "self", True)
+        t5 = coords.NeighbourTable(torch.zeros((125, n), dtype=torch.int32), 125, n)
+        km5 = coords.KernelMap(t5, n, n, t5, True)
         assert km5.tc_table() == (km5.nbr, None)                            # the 5x5x5 stem goes through im2col: not sorted
         assert km_1x1.tc_table() == (None, None) and km_1x1.tc_back_table() == (None, None)
     finally:

@@ -28,14 +28,6 @@ def fake_conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, b
     return cols if out_rows is None else torch.zeros_like(cols).index_copy_(0, out_rows.long(), cols)     # kept in fp64 for the comparison
 
 
-class Manager:
-    def __init__(self):
-        self.maps = {}
-
-    def kernel_map(self, *key):
-        return self.maps[key]
-
-
 @pytest.fixture()
 def patched(emu, monkeypatch):  # noqa: F811
     import gcdlss_b200
@@ -68,13 +60,12 @@ def scene():
     coarse, parent, code = ocd.stride2(c, 1)
     n, m = c.shape[0], coarse.shape[0]
     t3, tdown, tup = ocd.kmap_subm(c, 3, 1), ocd.kmap_down2(parent, code, m), ocd.kmap_up2(parent, code)
-    mgr = Manager()
     as_cols = lambda t: torch.from_numpy(np.ascontiguousarray(t.T))          # [kv, n_out] as the product stores it
-    km3 = coords.KernelMap(as_cols(t3), n, n, 27, mgr, "self", True)
-    km_down = coords.KernelMap(as_cols(tdown), n, m, 8, mgr, (2, 2, 2, True), False)
-    km_up = coords.KernelMap(as_cols(tup), m, n, 8, mgr, (1, 2, 2, False), False)
-    mgr.maps = {(2, 2, 2, True): km_up, (1, 2, 2, False): km_down}
-    return mgr, (km3, t3), (km_down, tdown), (km_up, tup)
+    n3, ndn, nup = coords.NeighbourTable(as_cols(t3), 27, n), coords.NeighbourTable(as_cols(tdown), 8, m), coords.NeighbourTable(as_cols(tup), 8, n)
+    km3 = coords.KernelMap(n3, n, n, n3, True)
+    km_down = coords.KernelMap(ndn, n, m, nup, False)
+    km_up = coords.KernelMap(nup, m, n, ndn, False)
+    return None, (km3, t3), (km_down, tdown), (km_up, tup)
 
 
 @pytest.mark.parametrize("which", ["subm", "down", "up"])

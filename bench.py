@@ -417,14 +417,11 @@ def run_ours(args):
     if rank == 0:
         mgr = cap_st.coordinate_manager
         pair_count = {}
-        for km in mgr._kmaps.values():
-            if km.nbr is not None:
-                n_pairs = km.num_pairs()
-                pair_count[km.nbr.data_ptr()] = n_pairs
-                if km._pairs is not None:
-                    pair_count[km._pairs[0].data_ptr()] = n_pairs
-                if getattr(km, "_sorted", None) is not None:          # tile-sorted copy (GCDLSS_TILE_SORT=1): same pairs
-                    pair_count[km._sorted[0].data_ptr()] = n_pairs
+        for table in mgr._tables.values():               # every pointer a convolution launch may carry -> pairs of that table
+            if table.nbr is not None:
+                n_pairs = int(table.pairs[2][-1].item())
+                for t in table.device_tensors():
+                    pair_count[t.data_ptr()] = n_pairs
         classes = {}
         for kind_k, ptr, n_out, kv, c_in, c_out, fn in ops.kernel_timer.captured:
             pairs = n_out if ptr == 0 else pair_count.get(ptr, n_out)

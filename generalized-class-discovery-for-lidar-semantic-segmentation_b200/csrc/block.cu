@@ -64,6 +64,7 @@ int32_t unit_conv(const gcd_convbn* u, const void* in, int64_t ld_in, void* out,
   a.in_dtype = dtype; a.out_dtype = dtype; a.stats = nullptr;
   a.math_mode = u->w_packed_fwd ? GCD_MATH_BF16_TCGEN05 : GCD_MATH_FP32_SIMT;
   a.out_rows = u->out_rows;
+  a.tile_masks = u->tile_masks;
   return gcd_conv_forward(&a, stream);
 }
 
@@ -77,6 +78,7 @@ int32_t unit_dgrad(const gcd_convbn* u, const void* dy, void* dx, int32_t dtype,
   a.in_dtype = dtype; a.out_dtype = dtype; a.stats = nullptr;
   a.math_mode = u->w_packed_bwd ? GCD_MATH_BF16_TCGEN05 : GCD_MATH_FP32_SIMT;
   a.out_rows = u->back_out_rows;
+  a.tile_masks = u->back_tile_masks;
   return gcd_conv_forward(&a, stream);
 }
 

@@ -7,7 +7,8 @@
 namespace gcd {
 namespace {
 constexpr int kRedX = 32, kRedY = 8;        // reduction kernels: 32 channel lanes x 8 row lanes
-constexpr int kMaxChanIter = 16;            // supports up to 512 channels
+constexpr int kMaxChanIter = 32;            // supports up to 1024 channels (MinkUNet50/101 bottlenecks at tensor stride 16: 256 x 4)
+constexpr int kMaxChannels = kRedX * kMaxChanIter;
 
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_apply_vec_kernel(const T* __re
                                                                     float* __restrict__ invstd_out, const float* __restrict__ scale_in,
                                                                     const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
                                                                     int relu, T* __restrict__ y, int64_t ld_y) {
-  __shared__ float s_scale[512], s_shift[512];
+  __shared__ float s_scale[kMaxChannels], s_shift[kMaxChannels];
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     if (kTrain) {
       const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_vec_kernel(const T* 
                                                                         const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
                                                                         int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
                                                                         int64_t ld_dres, float* dgamma, float* dbeta) {
-  __shared__ float s_k[512], s_mean[512], s_is[512], s_sg[512], s_sgx[512];
+  __shared__ float s_k[kMaxChannels], s_mean[kMaxChannels], s_is[kMaxChannels], s_sg[kMaxChannels], s_sgx[kMaxChannels];
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     const float is = invstd[ch];
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_reduce_wide_kernel(const T
                                                                           const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                                                                           int rows_per_block, double* __restrict__ sums) {
   constexpr int V = VecW<T>::V;
-  __shared__ float s_mean[512], s_is[512];
+  __shared__ float s_mean[kMaxChannels], s_is[kMaxChannels];
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) { s_mean[ch] = mean[ch]; s_is[ch] = invstd[ch]; }
   __syncthreads();
   column_reduce2_wide<T, V, 2>(n, c, rows_per_block, sums, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __r
                                                                      const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
                                                                      int relu, T* __restrict__ y, int64_t ld_y, int rows_per_block) {
   constexpr int V = VecW<T>::V;
-  __shared__ float s_scale[512], s_shift[512];
+  __shared__ float s_scale[kMaxChannels], s_shift[kMaxChannels];
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     if (kTrain) {
       const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_wide_kernel(const T*
                                                                          int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
                                                                          int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
   constexpr int V = VecW<T>::V;
-  __shared__ float s_k[512], s_mean[512], s_is[512], s_sg[512], s_sgx[512];
+  __shared__ float s_k[kMaxChannels], s_mean[kMaxChannels], s_is[kMaxChannels], s_sg[kMaxChannels], s_sgx[kMaxChannels];
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     const float is = invstd[ch];
@@ -710,11 +711,11 @@ inline unsigned vec_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil
 // reductions end in one fp64 atomic per channel per block: few, fat blocks (about 4 per SM) keep the atomics rare
 inline int red_rows(int64_t n) { return (int)std::max<int64_t>(kVecRows, ceil_div(n, (int64_t)kNumSMs * 4)); }
 inline unsigned red_grid(int64_t n) { return (unsigned)std::max<int64_t>(1, ceil_div(n, red_rows(n))); }
-inline bool vec_shape_ok(int c) { return c % 4 == 0 && c >= 8 && c <= 512; }
+inline bool vec_shape_ok(int c) { return c % 4 == 0 && c >= 8 && c <= kMaxChannels; }
 // 16-byte path: V channels per thread, every leading dimension a multiple of V, every pointer 16-byte aligned
 template <typename T> bool wide_ok(int c, std::initializer_list<int64_t> lds, std::initializer_list<const void*> ptrs) {
   const int V = 16 / (int)sizeof(T);
-  if (c % V || c < 2 * V || c > 512) return false;
+  if (c % V || c < 2 * V || c > kMaxChannels) return false;
   for (int64_t ld : lds) if (ld % V) return false;
   for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) % 16)) return false;
   return true;
@@ -802,7 +803,7 @@ void launch_apply(bool train, const void* x, int64_t ld_x, int64_t n, int c, con
 extern "C" int32_t gcd_bn_apply(const void* x, int64_t ld_x, int64_t n, int32_t c, const float* scale, const float* shift,
                                 const void* residual, int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream) {
   if (n == 0) return GCD_OK;
-  GCD_REQUIRE(c >= 1 && c <= 512, "gcd_bn_apply: channel count %d out of range", c);
+  GCD_REQUIRE(c >= 1 && c <= kMaxChannels, "gcd_bn_apply: channel count %d out of range", c);
   cudaStream_t st = as_stream(stream);
   if (dtype == GCD_F32) launch_apply<float>(false, x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, residual, ld_res, relu, y, ld_y, st);
   else launch_apply<__nv_bfloat16>(false, x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, residual, ld_res, relu, y, ld_y, st);
@@ -814,7 +815,7 @@ extern "C" int32_t gcd_bn_apply_train(const void* x, int64_t ld_x, int64_t n, in
                                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                       float* mean, float* invstd, const void* residual, int64_t ld_res, int32_t relu, void* y,
                                       int64_t ld_y, int32_t dtype, void* stream) {
-  GCD_REQUIRE(stats && mean && invstd && c >= 1 && c <= 512, "gcd_bn_apply_train: bad arguments");
+  GCD_REQUIRE(stats && mean && invstd && c >= 1 && c <= kMaxChannels, "gcd_bn_apply_train: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (dtype == GCD_F32) launch_apply<float>(true, x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, nullptr, nullptr, residual, ld_res, relu, y, ld_y, st);
   else launch_apply<__nv_bfloat16>(true, x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, nullptr, nullptr, residual, ld_res, relu, y, ld_y, st);
@@ -877,7 +878,7 @@ extern "C" int32_t gcd_bn_backward_apply(const void* dy, int64_t ld_dy, const vo
                                          int64_t n, int32_t c, const float* mean, const float* invstd, const float* gamma,
                                          const double* sums, int32_t relu, int32_t training, void* dx, int64_t ld_dx, void* dres,
                                          int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream) {
-  GCD_REQUIRE(c >= 1 && c <= 512, "gcd_bn_backward_apply: channel count %d out of range", c);
+  GCD_REQUIRE(c >= 1 && c <= kMaxChannels, "gcd_bn_backward_apply: channel count %d out of range", c);
   cudaStream_t st = as_stream(stream);
   if (n > 0) {
     if (dtype == GCD_F32) launch_bwd_apply<float>(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, dx, ld_dx, dres, ld_dres, dgamma, dbeta, st);

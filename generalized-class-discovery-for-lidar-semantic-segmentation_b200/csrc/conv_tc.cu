@@ -60,6 +60,7 @@ struct FwdParams {
   int stages;
   int group;                       // producer warps that share one stage (1, 2, 4, 8)
   const int32_t* out_rows;         // kPerm kernels: output row of table column i (tile-sorted table, tilesort.cu)
+  const uint32_t* tile_masks;      // optional: offsets with a hit per 128-column tile of nbr (tilesort.cu); the table warp then stages only those slices
 #ifdef GCD_TC_PROFILE
   long long* dbg;
   int ablate;                      // profile build only: 1 = no MMA issue, 2 = no gather copies, 4 = weight copies of 16 B
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
         mask &= mask - 1;
         if (mask == 0) { mask = lo_mask; lo_mask = 0; }
 #pragma unroll
-        for (int q = 0; q < (kNQ ? kNQ : 8); ++q) {
+        for (int q = 0; q < (kNQ ? kNQ : 16); ++q) {
           if (!kNQ && q >= nq) break;
           if (own_skip != 0) { --own_skip; continue; }
           own_skip = PA - 1;
@@ -230,19 +231,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     }
     cp_async_wait_all();                                 // nothing may still be writing smem at exit
 #ifdef GCD_TC_PROFILE
-    if (p.dbg && threadIdx.x == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; }
+    if (p.dbg && threadIdx.x == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; d[7] = tile_seq; }
 #endif
   } else if (warp == kTableWarp) {
     // ===================================================================== table warp
     // Stages the [kv][128] slice of the neighbour table of tile t + 1 while tile t is being processed (two buffers), works
     // out which offsets have a hit in the tile and publishes the tile's iteration count for the MMA warp.
     uint32_t tile_seq = 0;
+#ifdef GCD_TC_PROFILE
+    long long prof_twait = 0; const long long prof_t0 = clock64();
+#endif
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
       const uint32_t tb = tile_seq & 1;
+#ifdef GCD_TC_PROFILE
+      const long long ctw0 = clock64();
+#endif
       if (tile_seq >= 2) mbar_wait(&table_free[tb], ((tile_seq - 2) >> 1) & 1);
+#ifdef GCD_TC_PROFILE
+      prof_twait += clock64() - ctw0;
+#endif
       int32_t* dst = s_nbr0 + tb * (kMaxKV * kTileM);
       const int64_t r0 = (work / p.n_tiles_n) * kTileM + lane;
       uint32_t mask = 0;
+      if (p.tile_masks) {
+        // The tile's offsets are known (a tile of a sorted table uses 8-11 of 27, 1-3 of 8): stage only their slices, in
+        // one round of loads in most tiles instead of two rounds over the whole table slice.
+        mask = __ldg(&p.tile_masks[work / p.n_tiles_n]);
+        uint32_t todo = mask ? mask : 1u;                 // degenerate tile: offset 0 runs with all-zero rows
+        while (todo) {
+          int ks[14], v[14][4];
+#pragma unroll
+          for (int kk = 0; kk < 14; ++kk) {
+            ks[kk] = todo ? __ffs(todo) - 1 : -1;
+            todo &= todo - 1;                             // 0 & 0xffffffff stays 0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int64_t r = r0 + 32 * j;
+              v[kk][j] = -1;
+              if (ks[kk] >= 0 && r < p.n_out) v[kk][j] = __ldg(&p.nbr[(int64_t)ks[kk] * p.n_out + r]);
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 14; ++kk)
+            if (ks[kk] >= 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[ks[kk] * kTileM + lane + 32 * j] = v[kk][j];
+            }
+        }
+      } else
       for (int kb = 0; kb < p.kv; kb += 14) {             // 56 loads in flight per lane (a load per k would cost a memory latency each)
         int v[14][4];
 #pragma unroll
@@ -272,6 +308,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       __syncwarp();
       mbar_arrive_pred(&table_ready[tb], lane == 0 ? 1u : 0u);
     }
+#ifdef GCD_TC_PROFILE
+    if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[8] = clock64() - prof_t0; d[9] = prof_twait; }
+#endif
   } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
     // The whole warp runs the loop with warp-uniform values (so descriptors live in uniform registers and there is
@@ -331,17 +370,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       mma_commit_pred(&tmem_full[buf], leader ? 1u : 0u);
     }
 #ifdef GCD_TC_PROFILE
-    if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 8; d[4] = clock64() - prof_t0; d[5] = prof_full; d[6] = prof_acc; }
+    if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[4] = clock64() - prof_t0; d[5] = prof_full; d[6] = prof_acc; }
 #endif
   } else if (warp < kMmaWarp) {
     // ===================================================================== epilogue
     const int ew = warp - kEpilogueWarp0;      // == warp % 4: the TMEM lane quarter this warp may read
     uint32_t tile_seq = 0;
+#ifdef GCD_TC_PROFILE
+    long long prof_ewait = 0; const long long prof_t0 = clock64();
+#endif
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
       const int64_t tm = work / p.n_tiles_n;
       const int tn = (int)(work - tm * p.n_tiles_n);
       const uint32_t buf = tile_seq & 1;
+#ifdef GCD_TC_PROFILE
+      const long long cew0 = clock64();
+#endif
       mbar_wait_warp(&tmem_full[buf], (tile_seq >> 1) & 1, 128);
+#ifdef GCD_TC_PROFILE
+      prof_ewait += clock64() - cew0;
+#endif
       tc_fence_after();
       const int64_t row = tm * kTileM + ew * 32 + lane;
       int64_t orow = row;                        // where this accumulator lane's row goes
@@ -377,6 +425,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
+#ifdef GCD_TC_PROFILE
+    if (p.dbg && ew == 0 && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[10] = clock64() - prof_t0; d[11] = prof_ewait; }
+#endif
   }
 
   tc_fence_before();
@@ -688,7 +739,7 @@ static long long* g_debug_buffer = nullptr;
 
 bool conv_forward_tc_supported(const gcd_conv_args* a) {
   return a->in_dtype == GCD_BF16 && a->c_in % 16 == 0 && a->c_out % 16 == 0 && a->c_in >= 16 && a->c_out >= 16 &&
-         a->c_out <= 512 && a->kv <= kMaxKV && a->w_packed != nullptr && a->ld_in % 8 == 0 &&
+         a->c_out <= 1024 && a->c_in <= 1024 && a->kv <= kMaxKV && a->w_packed != nullptr && a->ld_in % 8 == 0 &&
          (reinterpret_cast<uintptr_t>(a->in) & 15) == 0 &&
          (a->out_dtype == GCD_BF16 ? (a->ld_out % 8 == 0) : (a->ld_out % 4 == 0)) && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0;
 }
@@ -744,7 +795,9 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   GCD_REQUIRE(a->ld_in > 0 && a->ld_in < (int64_t(1) << 31), "conv_forward_tc: input row pitch out of range");
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
   p.out_rows = a->out_rows;
+  p.tile_masks = a->tile_masks;
   GCD_REQUIRE(a->out_rows == nullptr || a->nbr != nullptr, "conv_forward_tc: out_rows needs a neighbour table");
+  GCD_REQUIRE(a->tile_masks == nullptr || a->nbr != nullptr, "conv_forward_tc: tile_masks needs a neighbour table");
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
   int stages = (kSmemBudget - 1024 - 2 * kMaxKV * kTileM * 4 - 512) / stage_bytes;
   stages = std::min(stages, kMaxStages);
@@ -762,7 +815,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   const int nq_sel = (a->c_in + kChunkK - 1) / kChunkK;
   const FwdKernel kernel = p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel);
   if (const cudaError_t e = tc_kernels_opt_in(); e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcgen05 kernels)");
-  if (a->c_in > 8 * kChunkK) { set_error("conv_forward_tc: more than 512 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
+  if (a->c_in > 16 * kChunkK) { set_error("conv_forward_tc: more than 1024 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;
   const unsigned grid = (unsigned)std::min<int64_t>(n_work, kNumSMs);
   kernel<<<grid, kTcThreads, smem, st>>>(p);
@@ -804,5 +857,5 @@ extern "C" int32_t gcd_debug_set_buffer(void* device_buffer) { gcd::g_debug_buff
 #endif
 
 extern "C" int32_t gcd_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t kv) {
-  return c_in % 16 == 0 && c_out % 16 == 0 && c_in >= 16 && c_out >= 16 && c_out <= 512 && kv <= 27;
+  return c_in % 16 == 0 && c_out % 16 == 0 && c_in >= 16 && c_out >= 16 && c_out <= 1024 && c_in <= 1024 && kv <= 27;
 }

@@ -23,6 +23,21 @@ __global__ void __launch_bounds__(kThreads) tile_sort_permute_kernel(const int32
                                                                       const int32_t* __restrict__ rows, int32_t* __restrict__ sorted) {
   tile_sort_permute_thread((int64_t)blockIdx.x * blockDim.x + threadIdx.x, nbr, n, kv, rows, sorted);
 }
+// One warp per 128-column tile of the sorted table: OR of the tile's (sorted) keys -> mask of offsets with a hit.
+__global__ void __launch_bounds__(kThreads) tile_masks_kernel(const unsigned long long* __restrict__ keys_sorted, int64_t n, int kv,
+                                                               uint32_t* __restrict__ masks) {
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tile * 128 >= n) return;
+  uint32_t acc = 0;                                  // keys have at most 27 bits
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t o = tile * 128 + lane + 32 * j;
+    if (o < n) acc |= (uint32_t)keys_sorted[o];
+  }
+  acc = __reduce_or_sync(0xffffffffu, acc);
+  if (lane == 0) masks[tile] = tile_mask_from_keys(acc, kv);
+}
 }  // namespace
 }  // namespace gcd
 
@@ -34,7 +49,7 @@ extern "C" size_t gcd_tile_sort_workspace_bytes(int64_t n) {
 }
 
 extern "C" int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows,
-                                      void* workspace, size_t workspace_bytes, void* stream) {
+                                      uint32_t* tile_masks, void* workspace, size_t workspace_bytes, void* stream) {
   GCD_REQUIRE(kv == 27 || kv == 8, "gcd_kmap_tile_sort: only 3x3x3 and 2x2x2 tables (kv = 27, 8) are sorted (got %d)", kv);
   GCD_REQUIRE(n >= 0 && n * (int64_t)kv < (1ll << 31), "gcd_kmap_tile_sort: table too large");
   GCD_REQUIRE(nbr && nbr_sorted && out_rows, "gcd_kmap_tile_sort: null pointer");
@@ -48,6 +63,8 @@ extern "C" int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv,
   const int32_t rc = radix_sort_pairs(reinterpret_cast<uint64_t*>(keys), out_rows, n, kv, p, radix_sort_workspace_bytes(n), st);
   if (rc != GCD_OK) return rc;
   tile_sort_permute_kernel<<<(unsigned)ceil_div(n * kv, kThreads), kThreads, 0, st>>>(nbr, n, kv, out_rows, nbr_sorted);
+  if (tile_masks)      // the sorted keys are still in the workspace: one warp per tile ORs 128 of them
+    tile_masks_kernel<<<(unsigned)ceil_div(ceil_div(n, 128) * 32, kThreads), kThreads, 0, st>>>(keys, n, kv, tile_masks);
   GCD_LAUNCH_CHECK("gcd_kmap_tile_sort");
   return GCD_OK;
 }

@@ -48,6 +48,16 @@ GCD_DEVFN void tile_sort_key8_thread(int64_t o, const int32_t* nbr, int64_t n, u
   vals[o] = (int32_t)o;
 }
 
+// Offsets with at least one hit among the columns whose keys were OR-ed into ``key_or``, as a mask with bit k = offset k
+// (the layout the convolution kernel walks): undoes the key's bit order for 3x3x3 tables.
+GCD_DEVFN uint32_t tile_mask_from_keys(unsigned long long key_or, int kv) {
+  if (kv != 27) return (uint32_t)key_or;
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) mask |= (uint32_t)((key_or >> tile_sort_bit(k)) & 1ull) << k;
+  return mask;
+}
+
 // sorted[k][i] = nbr[k][rows[i]]: writes coalesced, reads gathered (once per kernel map).
 GCD_DEVFN void tile_sort_permute_thread(int64_t t, const int32_t* nbr, int64_t n, int kv, const int32_t* rows, int32_t* sorted) {
   if (t >= n * kv) return;

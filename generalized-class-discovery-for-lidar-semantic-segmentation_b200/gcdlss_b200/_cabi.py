@@ -13,6 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
 LIB_PATH = os.path.join(_HERE, "libgcdlss_sm100a.so")
+_LIB_OVERRIDE = os.environ.get("GCDLSS_LIB_PATH")       # tuning only: the PROFILE=1 build (csrc/Makefile), loaded as is
 
 F32, BF16 = 0, 1
 MATH_FP32_SIMT, MATH_BF16_TC = 0, 1
@@ -58,7 +59,7 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64),
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
         ("stats", C.c_void_p), ("math_mode", C.c_int32),
-        ("out_rows", C.c_void_p),
+        ("out_rows", C.c_void_p), ("tile_masks", C.c_void_p),
     ]
 
 
@@ -87,6 +88,7 @@ class ConvBnUnit(C.Structure):
         ("stats", C.c_void_p), ("sums", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
         ("dw", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("out_rows", C.c_void_p), ("back_out_rows", C.c_void_p),
+        ("tile_masks", C.c_void_p), ("back_tile_masks", C.c_void_p),
     ]
 
 
@@ -130,7 +132,7 @@ PROTOTYPES = {
     "gcd_runtable_build": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     "gcd_kmap_subm_runs": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
     "gcd_tile_sort_workspace_bytes": (_sz, [_i64]),
-    "gcd_kmap_tile_sort": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "gcd_kmap_tile_sort": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gcd_pairs_workspace_bytes": (_sz, [_i64, _i32]),
     "gcd_pairs_from_table": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gcd_conv_forward": (_i32, [C.POINTER(ConvArgs), _vp]),
@@ -166,8 +168,8 @@ def lib():
     """The loaded library (built on first use if the .so is missing or older than its sources)."""
     global _lib
     if _lib is None:
-        path = LIB_PATH
-        if not os.path.exists(path) or (_stale() and shutil.which("nvcc")):
+        path = _LIB_OVERRIDE or LIB_PATH
+        if not _LIB_OVERRIDE and (not os.path.exists(path) or (_stale() and shutil.which("nvcc"))):
             path = build()
         handle = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():

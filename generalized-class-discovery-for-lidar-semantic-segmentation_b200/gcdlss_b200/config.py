@@ -25,10 +25,10 @@ def get_math_mode() -> str:
 
 # Kernel-map search of the stride-1 convolutions.  "points": one hash slot per voxel (gcd_hash_build + gcd_kmap_subm).
 # "runs": one 32-byte slot per run of four x-adjacent cells (gcd_runtable_build + gcd_kmap_subm_runs, csrc/runtable.cuh):
-# the same maps from 2.4-2.8x fewer scattered loads.  The run table's logic is held to the oracle on the CPU by
-# tests/test_emulated_kernels.py; it becomes the default once tests/test_gpu_zzz_runtable.py has passed on a B200.
+# the same maps from 2.4-2.8x fewer scattered loads.  Default since the whole GPU suite passed under it on a B200 (round 2,
+# profiles/r2_call1_tests.txt); the run table's logic is also held to the oracle on the CPU by tests/test_emulated_kernels.py.
 _KMAP = ("points", "runs")
-_state["kmap"] = os.environ.get("GCDLSS_KMAP", "points")
+_state["kmap"] = os.environ.get("GCDLSS_KMAP", "runs")
 if _state["kmap"] not in _KMAP:
     raise ValueError(f"GCDLSS_KMAP must be one of {_KMAP}")
 
@@ -44,10 +44,10 @@ def get_kmap_search() -> str:
 
 
 # Tile sort of the 3x3x3 neighbour tables for the tcgen05 convolution (csrc/tilesort.cuh): columns sorted by the mask of
-# present neighbours so that a 128-column tile visits 8-12 kernel offsets instead of 21-25.  Opt-in until it has run on a
-# B200 (tests/test_gpu_zz_tilesort.py); maps with fewer rows than ``tile_sort_min_rows`` are left in scan order (the
-# sort is ~20 small launches per map).
-_state["tile_sort"] = os.environ.get("GCDLSS_TILE_SORT", "0") not in ("0", "")
+# present neighbours so that a 128-column tile visits 8-12 kernel offsets instead of 21-25.  On by default (every rank, every
+# workload: the whole GPU suite passes with it, profiles/r2_call1_tests.txt); maps with fewer rows than
+# ``tile_sort_min_rows`` are left in scan order (the sort is ~20 small launches per map).
+_state["tile_sort"] = os.environ.get("GCDLSS_TILE_SORT", "1") not in ("0", "")
 _state["tile_sort_min_rows"] = int(os.environ.get("GCDLSS_TILE_SORT_MIN_ROWS", "16384"))
 
 

@@ -31,14 +31,14 @@ class NeighbourTable:
 
     def __init__(self, nbr, kv, n_out):
         self.nbr, self.kv, self.n_out = nbr, kv, n_out
-        self._sorted = None          # (tile-sorted table, its column -> output row permutation)
+        self._sorted = None          # (tile-sorted table, its column -> output row permutation, per-tile offset masks)
         self._pairs = None
 
     def tc_table(self):
-        """(table, out_rows) for the tcgen05 convolution: the tile-sorted copy when tile sorting is on and this is a
-        3x3x3 or 2x2x2 table with enough rows to pay for the sort, else (nbr, None)."""
+        """(table, out_rows, tile_masks) for the tcgen05 convolution: the tile-sorted copy when tile sorting is on and this
+        is a 3x3x3 or 2x2x2 table with enough rows to pay for the sort, else (nbr, None, None)."""
         if self.nbr is None or self.kv not in (8, 27) or not config.get_tile_sort() or self.n_out < config.tile_sort_min_rows():
-            return self.nbr, None
+            return self.nbr, None, None
         if self._sorted is None:
             self._sorted = ops.kmap_tile_sort(self.nbr)
         return self._sorted
@@ -79,7 +79,7 @@ class KernelMap:
 
     def tc_back_table(self):
         """The same for the table that drives the matching dgrad."""
-        return self.back.tc_table() if self.back is not None else (None, None)
+        return self.back.tc_table() if self.back is not None else (None, None, None)
 
     @property
     def pairs(self):

@@ -89,9 +89,10 @@ def conv_fwd_impl(feats, weight, bias, kmap, out_dtype, holder):
             packed = holder._pk_fwd
         else:
             packed = ops.pack_weights(w3, False, False)
-    nbr, rows = kmap.tc_table() if tc else (kmap.nbr, None)
+    nbr, rows, masks = kmap.tc_table() if tc else (kmap.nbr, None, None)
     return ops.conv_forward(feats, nbr, w3, kmap.n_out, bias=bias.detach().reshape(-1) if bias is not None else None,
-                            out_dtype=out_dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed, out_rows=rows)
+                            out_dtype=out_dtype, math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed, out_rows=rows,
+                            tile_masks=masks)
 
 
 def conv_dgrad_impl(gout, weight, kmap, in_dtype, holder):
@@ -106,9 +107,9 @@ def conv_dgrad_impl(gout, weight, kmap, in_dtype, holder):
             packed = holder._pk_bwd
         else:
             packed = ops.pack_weights(w3, True, kmap.back_mirror)
-    back, rows = kmap.tc_back_table() if tc else (kmap.back_nbr, None)
+    back, rows, masks = kmap.tc_back_table() if tc else (kmap.back_nbr, None, None)
     return ops.conv_forward(g, back, w3, kmap.n_in, transpose_w=True, mirror=kmap.back_mirror, out_dtype=in_dtype,
-                            math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed, out_rows=rows)
+                            math_mode=MATH_BF16_TC if tc else MATH_FP32_SIMT, w_packed=packed, out_rows=rows, tile_masks=masks)
 
 
 def conv_wgrad_impl(feats, gout, weight, kmap, want_bias_grad=False):
@@ -249,9 +250,10 @@ _FUSED_C = __import__("os").environ.get("GCDLSS_FUSED_BLOCKS", "1") != "0"
 def _fill_unit(u, w, gamma, beta, bn, kmap, holder, tc, with_grad):
     w3 = _as3d(w)
     kv, c_in, c_out = w3.shape
-    nbr, rows = kmap.tc_table() if tc else (kmap.nbr, None)
+    nbr, rows, masks = kmap.tc_table() if tc else (kmap.nbr, None, None)
     u.nbr = nbr.data_ptr() if nbr is not None else None
     u.out_rows = rows.data_ptr() if rows is not None else None
+    u.tile_masks = masks.data_ptr() if masks is not None else None
     u.n_in, u.n_out = kmap.n_in, kmap.n_out
     u.kv, u.c_in, u.c_out = kv, c_in, c_out
     u.w = w.data_ptr()
@@ -264,9 +266,10 @@ def _fill_unit(u, w, gamma, beta, bn, kmap, holder, tc, with_grad):
     u.running_mean, u.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
     u.eps, u.momentum = bn.eps, bn.momentum
     if with_grad:
-        back, back_rows = kmap.tc_back_table() if tc else (kmap.back_nbr, None)
+        back, back_rows, back_masks = kmap.tc_back_table() if tc else (kmap.back_nbr, None, None)
         u.back_nbr = back.data_ptr() if back is not None else None
         u.back_out_rows = back_rows.data_ptr() if back_rows is not None else None
+        u.back_tile_masks = back_masks.data_ptr() if back_masks is not None else None
         u.back_mirror = int(kmap.back_mirror)
         if tc:
             u.w_packed_bwd = holder._pk_bwd.data_ptr()

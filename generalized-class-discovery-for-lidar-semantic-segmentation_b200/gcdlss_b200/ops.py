@@ -255,16 +255,18 @@ def kmap_subm_runs(coords: torch.Tensor, table: RunTable, kernel_size: int, ts: 
 
 
 def kmap_tile_sort(nbr: torch.Tensor):
-    """Tile-sorted copy of a 3x3x3 / 2x2x2 table for the tcgen05 convolution: (nbr_sorted [kv, n] = nbr[:, rows], rows [n] int32)."""
+    """Tile-sorted copy of a 3x3x3 / 2x2x2 table for the tcgen05 convolution:
+    (nbr_sorted [kv, n] = nbr[:, rows], rows [n] int32, tile_masks [ceil(n / 128)] int32: offsets with a hit per 128-column tile)."""
     kv, n = nbr.shape
     dev = nbr.device
     nbr_sorted = torch.empty_like(nbr)
     rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    masks = torch.empty(max((n + 127) // 128, 1), dtype=torch.int32, device=dev)
     ws_bytes = int(lib().gcd_tile_sort_workspace_bytes(n))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    call("gcd_kmap_tile_sort", _ptr(nbr), n, kv, _ptr(nbr_sorted), _ptr(rows), _ptr(ws), ws_bytes, _stream())
-    _count(22 if kv == 27 else 12)
-    return nbr_sorted, rows[:n]
+    call("gcd_kmap_tile_sort", _ptr(nbr), n, kv, _ptr(nbr_sorted), _ptr(rows), _ptr(masks), _ptr(ws), ws_bytes, _stream())
+    _count(23 if kv == 27 else 13)
+    return nbr_sorted, rows[:n], masks
 
 
 def kmap_down2(parent, code, n_coarse: int) -> torch.Tensor:
@@ -318,12 +320,12 @@ def pack_weights_batched(desc_table_dev: torch.Tensor, n_descs: int, total_block
 
 
 def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=MATH_FP32_SIMT,
-                 w_packed=None, stats=None, out_rows=None):
+                 w_packed=None, stats=None, out_rows=None, tile_masks=None):
     """out[o] = sum_k inp[nbr[k, o]] @ B_k, B_k = w3[k] (or w3[wsel(k)]^T when transpose_w).
 
     inp [n_in, c_in'] row-major; nbr [kv, n_out] int32 or None (identity); w3 fp32 [kv, c_in, c_out].
     ``out_rows`` (tcgen05 path only): ``nbr`` is a tile-sorted table (:func:`kmap_tile_sort`) and column i of it is
-    output row out_rows[i].
+    output row out_rows[i]; ``tile_masks``: its per-tile offset masks.
     """
     _require_cuda(inp, w3)
     inp = _rowmajor(inp)
@@ -350,13 +352,14 @@ def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, b
     a.stats = stats.data_ptr() if stats is not None else None
     a.math_mode = math_mode
     a.out_rows = out_rows.data_ptr() if out_rows is not None else None
+    a.tile_masks = tile_masks.data_ptr() if tile_masks is not None else None
     kind = "conv_tc" if math_mode == MATH_BF16_TC else "conv_simt"
     end = kernel_timer.bracket(kind, nbr, n_out, kv, k_dim, n_dim)
     call("gcd_conv_forward", C.byref(a), _stream())
     if end is not None:
         end.record()
     if kernel_timer.capture:
-        keep = (inp, nbr, w3, w_packed, bias, out, out_rows)        # keeps the operands alive for the replay
+        keep = (inp, nbr, w3, w_packed, bias, out, out_rows, tile_masks)        # keeps the operands alive for the replay
         kernel_timer.remember(kind, nbr, n_out, kv, k_dim, n_dim, lambda a=a, keep=keep: call("gcd_conv_forward", C.byref(a), _stream()))
     _count()
     return out

@@ -63,24 +63,71 @@ def stage1_step(model, feats, bcoords, labels):
     return point_cross_entropy(out["logits"], labels.long())
 
 
+def _pitch_bands(points, lo: float, hi: float, edges):
+    """Band index of every point: band i covers (angle_list[i + 1], angle_list[i]] of the clamped pitch angle, exactly the
+    reference's comparisons (ref exp_merge_mean_teacher.py:1735-1765: float32 pitch against the float64 ``np.linspace`` edges,
+    which torch compares in float32), counted instead of masked: band = number of interior edges at or above the pitch."""
+    rho = torch.sqrt(points[:, 0] ** 2 + points[:, 1] ** 2)
+    pitch = torch.clamp(torch.atan2(points[:, 2], rho), lo + 1e-5, hi - 1e-5)
+    band = torch.zeros(points.shape[0], dtype=torch.int64, device=points.device)
+    for e in edges[1:-1]:
+        band += pitch <= float(e)
+    return band
+
+
 def laser_mix(points_sup, points_unsup, feats_sup, feats_unsup, labels_sup, labels_unsup, num_areas: int,
-              pitch_angles=(-25.0, 3.0)):
-    """Pitch-angle band swap between one labelled and one unlabelled scan (ref exp_merge_mean_teacher.py:1731-1787).
-    Points are [P, 3] sensor-frame xyz.  Returns two mixed scans (points, feats, labels)."""
-    lo, hi = pitch_angles[0] / 180 * math.pi, pitch_angles[1] / 180 * math.pi
+              pitch_angles=(-25, 3), return_split: bool = True):
+    """Pitch-angle band swap between one labelled and one unlabelled scan, row for row what
+    ``laser_mix_transform`` returns (ref exp_merge_mean_teacher.py:1731-1787): mix 1 is, band by band from the top,
+    the labelled scan's points of the even bands and the unlabelled scan's points of the odd bands (each band's points in
+    their original order); mix 2 is the complement.  Points are [P, 3] sensor-frame xyz.
 
-    def band(p):
-        pitch = torch.atan2(p[:, 2], torch.sqrt(p[:, 0] ** 2 + p[:, 1] ** 2)).clamp(lo + 1e-5, hi - 1e-5)
-        # angle_list = linspace(hi, lo, num_areas + 1); band i covers (angle[i+1], angle[i]]
-        return torch.clamp(((hi - pitch) / (hi - lo) * num_areas).floor().long(), 0, num_areas - 1)
+    The reference builds 4 * num_areas boolean-mask selections (a device->host sync each); here every point gets the key
+    ``mix * 8 + band`` and ONE stable sort of the keys yields both mixes, bands in order, original order inside a band (a
+    band of a mix comes from one source only, so the sort never has to order the two sources against each other).
+    ``return_split=False`` returns the sorted rows and their mix index without splitting (no host sync at all)."""
+    import numpy as np
+    lo, hi = pitch_angles[0] / 180 * np.pi, pitch_angles[1] / 180 * np.pi
+    edges = np.linspace(hi, lo, num_areas + 1)
+    bs, bu = _pitch_bands(points_sup, lo, hi, edges), _pitch_bands(points_unsup, lo, hi, edges)
+    key = torch.cat([(bs % 2) * 8 + bs, (1 - bu % 2) * 8 + bu])             # labelled: even band -> mix 1 (index 0); unlabelled: odd band -> mix 1
+    key, order = torch.sort(key, stable=True)
+    pts = torch.cat([points_sup, points_unsup]).index_select(0, order)
+    feats = torch.cat([feats_sup, feats_unsup]).index_select(0, order)
+    labels = torch.cat([labels_sup, labels_unsup.to(labels_sup.dtype)]).index_select(0, order)
+    mix = key >> 3
+    if not return_split:
+        return pts, feats, labels, mix
+    n1 = int((mix == 0).sum())
+    return (pts[:n1], feats[:n1], labels[:n1]), (pts[n1:], feats[n1:], labels[n1:])
 
-    bs, bu = band(points_sup), band(points_unsup)
-    even_s, even_u = (bs % 2 == 0), (bu % 2 == 0)
-    mix1 = (torch.cat([points_sup[even_s], points_unsup[~even_u]]), torch.cat([feats_sup[even_s], feats_unsup[~even_u]]),
-            torch.cat([labels_sup[even_s], labels_unsup[~even_u]]))
-    mix2 = (torch.cat([points_unsup[even_u], points_sup[~even_s]]), torch.cat([feats_unsup[even_u], feats_sup[~even_s]]),
-            torch.cat([labels_unsup[even_u], labels_sup[~even_s]]))
-    return mix1, mix2
+
+def mix_transform(sup_data, unsup_data, mix_unsup_pseudo_labels, num_areas, pitch_angles=(-25, 3)):
+    """Point assembly of the reference's ``mix_transform`` (ref exp_merge_mean_teacher.py:1577-1729) with the same
+    arguments: ``sup_data`` / ``unsup_data`` are the collated point-level dicts ('coords' [P, 4] float (batch, x, y, z),
+    'feats' [P, C], sup also 'mapped_labels' [P]); scan 0 of the labelled half is mixed with scan 0 of the unlabelled half
+    and, when both halves hold the same number of scans, everything else of one half with everything else of the other
+    (``coords[:, 0] != 0``: the reference is written for two scans per half).  ``num_areas``: the band counts the reference
+    draws with ``np.random.choice(semi_train_cfg['num_areas'])``, one per LaserMix call, passed in so that the caller owns
+    the randomness.  Returns (mix_bcoords float32 [Q, 4], mix_feats float32 [Q, C], mix_labels int32 [Q]) with batch
+    indices 0, 1 (, 2, 3), row for row the reference's arrays, and everything stays on the device."""
+    sc, uc = sup_data["coords"], unsup_data["coords"]
+    first_s, first_u = sc[:, 0] == 0, uc[:, 0] == 0
+    n_first_s, n_first_u = int(first_s.sum()), int(first_u.sum())
+    labels, pseudo = sup_data["mapped_labels"], mix_unsup_pseudo_labels
+    pairs = [(sc[first_s][:, 1:], uc[first_u][:, 1:], sup_data["feats"][first_s], unsup_data["feats"][first_u],
+              labels[:n_first_s], pseudo[:n_first_u])]
+    if len(torch.unique(sc[:, 0])) == len(torch.unique(uc[:, 0])):
+        pairs.append((sc[~first_s][:, 1:], uc[~first_u][:, 1:], sup_data["feats"][~first_s], unsup_data["feats"][~first_u],
+                      labels[n_first_s:], pseudo[n_first_u:]))
+    areas = list(num_areas) if isinstance(num_areas, (list, tuple)) else [num_areas] * len(pairs)
+    rows, feats, labs = [], [], []
+    for i, (ps, pu, fs, fu, ls, lu) in enumerate(pairs):
+        p, f, l, mix = laser_mix(ps, pu, fs, fu, ls, lu, int(areas[i]), pitch_angles, return_split=False)
+        rows.append(torch.cat([(2 * i + mix).to(p.dtype)[:, None], p], 1))
+        feats.append(f)
+        labs.append(l)
+    return torch.cat(rows).float(), torch.cat(feats).float(), torch.cat(labs).int()
 
 
 class Stage2Harness:

@@ -158,10 +158,12 @@ int32_t gcd_kmap_subm_runs(const int32_t* coords, int64_t n, const void* slots, 
  * columns sorted (stably) by the mask of present neighbours (3x3x3: rarest offsets in the top bits), so that the
  * 128-column tiles of the kernel see 8-12 offsets with a hit instead of 21-25 (2x2x2: 1-4 instead of 7-8)
  * (csrc/tilesort.cuh).  nbr_sorted [kv][n] = nbr[:, out_rows], out_rows [n] the permutation; pass both to
- * gcd_conv_forward (nbr = nbr_sorted, out_rows).  Pair lists are still built from nbr. */
+ * gcd_conv_forward (nbr = nbr_sorted, out_rows).  Pair lists are still built from nbr.
+ * tile_masks (optional, [ceil(n / 128)] uint32): bit k of entry t is set iff some column of tile t of nbr_sorted has a
+ * neighbour at offset k; gcd_conv_args.tile_masks lets the kernel stage only those slices of the table. */
 size_t gcd_tile_sort_workspace_bytes(int64_t n);
 int32_t gcd_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           uint32_t* tile_masks, void* workspace, size_t workspace_bytes, void* stream);
 
 size_t gcd_pairs_workspace_bytes(int64_t n_out, int32_t kv);
 /* Per-offset pair lists of a table: pairs of offset k are [pair_off[k], pair_off[k+1]), sorted by
@@ -201,6 +203,8 @@ typedef struct {
   int32_t math_mode;     /* gcd_math_mode */
   const int32_t* out_rows; /* optional (tcgen05 path only): nbr is a tile-sorted table (gcd_kmap_tile_sort) and the
                               result of table column i is written to row out_rows[i] of out; NULL = row i */
+  const uint32_t* tile_masks; /* optional (tcgen05 path only): per 128-column tile of nbr, the mask of offsets with a hit
+                                 (gcd_kmap_tile_sort); NULL = the kernel derives it from the whole table slice */
 } gcd_conv_args;
 
 int32_t gcd_conv_forward(const gcd_conv_args* args, void* stream);
@@ -336,6 +340,8 @@ typedef struct {
   float* dw; float* dgamma; float* dbeta;    /* zero on entry of backward, accumulated into */
   const int32_t* out_rows;       /* optional: nbr is tile-sorted (see gcd_conv_args.out_rows); tcgen05 units only */
   const int32_t* back_out_rows;  /* optional: the same for back_nbr */
+  const uint32_t* tile_masks;      /* optional: per-tile offset masks of nbr (see gcd_conv_args.tile_masks) */
+  const uint32_t* back_tile_masks; /* optional: the same for back_nbr */
 } gcd_convbn;
 
 typedef struct {

@@ -8,6 +8,7 @@
 
 extern "C" {
 int32_t emu_tile_sort_bit(int32_t k) { return gcd::tile_sort_bit(k); }
+uint32_t emu_tile_mask_from_keys(unsigned long long key_or, int32_t kv) { return gcd::tile_mask_from_keys(key_or, kv); }
 
 void emu_kmap_tile_sort(const int32_t* nbr, int64_t n, int32_t kv, int32_t* nbr_sorted, int32_t* out_rows, unsigned long long* keys_out) {
   std::vector<unsigned long long> keys(n);

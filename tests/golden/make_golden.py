@@ -166,10 +166,78 @@ def part3_tile_sort():
     print("tile_sort_frozen.npz:", {k: v.shape for k, v in out.items()})
 
 
+def reference_lasermix_methods():
+    """``mix_transform`` and ``laser_mix_transform`` of ExpMergeDiscover_LaserMix_MeanTeacher
+    (/root/reference/modules/exp_merge_mean_teacher.py:1577-1787), taken from the file by AST and executed unchanged (the module
+    itself cannot be imported: pytorch_lightning / MinkowskiEngine are not installable)."""
+    src = open(os.path.join(REF, "modules", "exp_merge_mean_teacher.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "torch": torch}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "ExpMergeDiscover_LaserMix_MeanTeacher":
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in ("mix_transform", "laser_mix_transform"):
+                    exec(textwrap.dedent(ast.get_source_segment(src, item)), ns)
+
+    class Holder:
+        semi_train_cfg = dict(pitch_angles=[-25, 3], num_areas=[3, 4, 5, 6])      # ref :1448-1452
+        mix_transform = ns["mix_transform"]
+        laser_mix_transform = ns["laser_mix_transform"]
+    return Holder()
+
+
+def lasermix_inputs(seed, n_sup_scans, n_unsup_scans, n_points):
+    """Point-level dicts as the Stage-2 collate hands them to ``mix_transform`` (batched float coords [P, 4], feats [P, 1],
+    labels [P]); scans look like a ground plane + clutter seen from 1.7 m so that every pitch band is populated."""
+    rng = np.random.default_rng(seed)
+
+    def scans(n_scans):
+        c, f = [], []
+        for b in range(n_scans):
+            n = n_points + int(rng.integers(0, 200))
+            az = rng.uniform(-np.pi, np.pi, n)
+            pitch = np.deg2rad(rng.uniform(-30.0, 6.0, n))           # a little beyond [-25, 3]: exercises the clamp
+            r = rng.uniform(2.0, 60.0, n)
+            xyz = np.stack([r * np.cos(pitch) * np.cos(az), r * np.cos(pitch) * np.sin(az), r * np.sin(pitch)], 1).astype(np.float32)
+            c.append(np.concatenate([np.full((n, 1), b, np.float32), xyz], 1))
+            f.append(rng.uniform(0, 1, (n, 1)).astype(np.float32))
+        return np.concatenate(c), np.concatenate(f)
+
+    sc, sf = scans(n_sup_scans)
+    uc, uf = scans(n_unsup_scans)
+    sup_labels = rng.integers(0, 17, sc.shape[0]).astype(np.int64)
+    pseudo = rng.integers(-1, 17, uc.shape[0]).astype(np.int64)
+    return sc, sf, sup_labels, uc, uf, pseudo
+
+
+def part4_lasermix():
+    """Freezes the reference's LaserMix outputs (row order, band edges, labels) and the quantisation of the mixed batch."""
+    ref = reference_lasermix_methods()
+    out = {}
+    for tag, (seed, ns, nu, n) in {"b22": (7, 2, 2, 4000), "b21": (8, 2, 1, 2500), "b22_small": (9, 2, 2, 37)}.items():
+        sc, sf, sl, uc, uf, pl = lasermix_inputs(seed, ns, nu, n)
+        np.random.seed(100 + seed)
+        areas = [int(np.random.choice([3, 4, 5, 6], size=1)[0]) for _ in range(2)]     # what the calls below will draw
+        np.random.seed(100 + seed)
+        sup = {"coords": torch.from_numpy(sc), "feats": torch.from_numpy(sf), "mapped_labels": torch.from_numpy(sl)}
+        unsup = {"coords": torch.from_numpy(uc), "feats": torch.from_numpy(uf)}
+        bcoords, feats, labels = ref.mix_transform(sup, unsup, torch.from_numpy(pl))
+        # the Stage-2 step quantises the mixed batch inline, batch column included (ref :2856-2861)
+        qc, um, inv = oq.sparse_quantize_me(bcoords.numpy(), 0.05)
+        for k, v in dict(sup_coords=sc, sup_feats=sf, sup_labels=sl, unsup_coords=uc, unsup_feats=uf, pseudo=pl, areas=np.asarray(areas),
+                         mix_bcoords=bcoords.numpy(), mix_feats=feats.numpy(), mix_labels=labels.numpy(), q_coords=qc, q_umap=um, q_inv=inv).items():
+            out[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "lasermix_pinned.npz"), **out)
+    print("lasermix_pinned.npz:", {k: v.shape for k, v in out.items() if "mix_bcoords" in k})
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["tile_sort"]:           # derived from oracle_frozen.npz alone: does not need the reference checkout
+    if sys.argv[1:] == ["lasermix"]:
+        part4_lasermix()
+    elif sys.argv[1:] == ["tile_sort"]:           # derived from oracle_frozen.npz alone: does not need the reference checkout
         part3_tile_sort()
     else:
         part1_reference()
         part2_oracle()
         part3_tile_sort()
+        part4_lasermix()

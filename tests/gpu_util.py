@@ -57,9 +57,9 @@ class OpChecker:
             return dx, dres, dgamma, dbeta
 
         def conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=0, w_packed=None,
-                         stats=None, out_rows=None):
+                         stats=None, out_rows=None, tile_masks=None):
             out = real_conv_fwd(inp, nbr, w3, n_out, transpose_w=transpose_w, mirror=mirror, bias=bias, out_dtype=out_dtype,
-                                math_mode=math_mode, w_packed=w_packed, stats=stats, out_rows=out_rows)
+                                math_mode=math_mode, w_packed=w_packed, stats=stats, out_rows=out_rows, tile_masks=tile_masks)
             kv = w3.shape[0]
             ref = torch.zeros((n_out, out.shape[1]), dtype=torch.float64, device=inp.device)
             x = inp.double()

@@ -11,7 +11,7 @@ from conftest import small_cloud
 from gpu_util import TOL_BF16, OpChecker, rel_err
 from oracle import coords as ocd
 from oracle import quantize as oq
-from test_tile_sort_model import sort_reference
+from test_tile_sort_model import sort_reference, tile_masks_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -39,10 +39,11 @@ def test_sort_equals_numpy(cuda, n):
     from gcdlss_b200 import ops
     c = small_cloud(n, n, spread=0.4, batch=0)
     nbr = np.ascontiguousarray(ocd.kmap_subm(c, 3, 1).T)
-    got, rows = ops.kmap_tile_sort(torch.from_numpy(nbr).cuda())
+    got, rows, masks = ops.kmap_tile_sort(torch.from_numpy(nbr).cuda())
     ref, ref_rows, _ = sort_reference(nbr)
     np.testing.assert_array_equal(rows.cpu().numpy(), ref_rows)
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    np.testing.assert_array_equal(masks.cpu().numpy(), tile_masks_reference(ref))
 
 
 def test_sort_of_stride2_tables_equals_numpy(cuda):
@@ -51,10 +52,11 @@ def test_sort_of_stride2_tables_equals_numpy(cuda):
     coarse, parent, code = ocd.stride2(c, 1)
     for nbr in (ocd.kmap_down2(parent, code, coarse.shape[0]), ocd.kmap_up2(parent, code)):
         cols = np.ascontiguousarray(nbr.T)
-        got, rows = ops.kmap_tile_sort(torch.from_numpy(cols).cuda())
+        got, rows, masks = ops.kmap_tile_sort(torch.from_numpy(cols).cuda())
         ref, ref_rows, _ = sort_reference(cols)
         np.testing.assert_array_equal(rows.cpu().numpy(), ref_rows)
         np.testing.assert_array_equal(got.cpu().numpy(), ref)
+        np.testing.assert_array_equal(masks.cpu().numpy(), tile_masks_reference(ref))
 
 
 def test_sort_against_the_frozen_permutations(cuda, oracle_frozen):
@@ -65,7 +67,7 @@ def test_sort_against_the_frozen_permutations(cuda, oracle_frozen):
     frozen = np.load(os.path.join(GOLDEN, "tile_sort_frozen.npz"))
     for name, table in frozen_tables(oracle_frozen).items():
         table = np.ascontiguousarray(table, np.int32)
-        got, rows = ops.kmap_tile_sort(torch.from_numpy(table).cuda())
+        got, rows, _ = ops.kmap_tile_sort(torch.from_numpy(table).cuda())
         np.testing.assert_array_equal(rows.cpu().numpy(), frozen[f"rows_{name}"])
         np.testing.assert_array_equal(got.cpu().numpy(), table[:, frozen[f"rows_{name}"]])
 
@@ -76,14 +78,17 @@ def test_conv_forward_and_dgrad_with_sorted_table(cuda, tile_sort, cin, cout):
     from gcdlss_b200.coords import CoordinateManager
     bc = kitti_coords()
     km = CoordinateManager(torch.from_numpy(bc).cuda()).kernel_map(1, 3, 1, False)
-    table, rows = km.tc_table()
+    table, rows, masks = km.tc_table()
     assert rows is not None and table.data_ptr() != km.nbr.data_ptr()
     n = km.n_out
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(n, cin, device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn(27, cin, cout, device="cuda", generator=g) * 0.05
     plain = ops.conv_forward(x, km.nbr, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=ops.pack_weights(w, False, False))
-    tiled = ops.conv_forward(x, table, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=ops.pack_weights(w, False, False), out_rows=rows)
+    tiled = ops.conv_forward(x, table, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=ops.pack_weights(w, False, False), out_rows=rows,
+                             tile_masks=masks)
+    no_masks = ops.conv_forward(x, table, w, n, out_dtype=torch.bfloat16, math_mode=1, w_packed=ops.pack_weights(w, False, False), out_rows=rows)
+    assert torch.equal(tiled, no_masks), "the per-tile masks only tell the kernel which slices to stage: same offsets, same order, same bits"
     ref = torch.zeros(n, cout, dtype=torch.float64, device="cuda")
     for k in range(27):
         idx = km.nbr[k].long()
@@ -95,7 +100,8 @@ def test_conv_forward_and_dgrad_with_sorted_table(cuda, tile_sort, cin, cout):
     gy = torch.randn(n, cout, device="cuda", generator=g).to(torch.bfloat16)
     pk = ops.pack_weights(w, True, True)
     d_plain = ops.conv_forward(gy, km.nbr, w, n, transpose_w=True, mirror=True, out_dtype=torch.bfloat16, math_mode=1, w_packed=pk)
-    d_tiled = ops.conv_forward(gy, table, w, n, transpose_w=True, mirror=True, out_dtype=torch.bfloat16, math_mode=1, w_packed=pk, out_rows=rows)
+    d_tiled = ops.conv_forward(gy, table, w, n, transpose_w=True, mirror=True, out_dtype=torch.bfloat16, math_mode=1, w_packed=pk, out_rows=rows,
+                               tile_masks=masks)
     assert rel_err(d_tiled, d_plain) < TOL_BF16
 
 

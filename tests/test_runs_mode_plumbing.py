@@ -96,4 +96,4 @@ def test_kernel_maps_outlive_their_manager(runs_manager):
     np.testing.assert_array_equal(km_down.nbr.numpy().T, ocd.kmap_down2(parent, code, lv.coords[1].shape[0]))
     np.testing.assert_array_equal(km_down.back_nbr.numpy().T, ocd.kmap_up2(parent, code))
     assert km_down.tc_back_table()[0] is km_down.back_nbr
-    assert km_1x1.back_nbr is None and km_1x1.tc_back_table() == (None, None)
+    assert km_1x1.back_nbr is None and km_1x1.tc_back_table() == (None, None, None)

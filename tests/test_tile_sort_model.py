@@ -66,6 +66,34 @@ def emu_sort(emu, nbr_cols):
     return out, rows[:n], keys[:n]
 
 
+def tile_masks_reference(sorted_cols):
+    """Per 128-column tile: bit k set iff some column of the tile has a neighbour at offset k (numpy)."""
+    kv, n = sorted_cols.shape
+    out = np.zeros((n + 127) // 128, np.uint32)
+    for t in range(out.shape[0]):
+        present = (sorted_cols[:, 128 * t:128 * t + 128] >= 0).any(1)
+        out[t] = sum(1 << k for k in range(kv) if present[k])
+    return out.view(np.int32)
+
+
+def emu_tile_masks(emu, sorted_keys, kv):
+    """The device code's mask of each tile from the OR of its sorted keys (csrc/tilesort.cuh:tile_mask_from_keys)."""
+    emu.emu_tile_mask_from_keys.restype = C.c_uint32
+    n = sorted_keys.shape[0]
+    out = np.zeros((n + 127) // 128, np.uint32)
+    for t in range(out.shape[0]):
+        out[t] = emu.emu_tile_mask_from_keys(C.c_ulonglong(int(np.bitwise_or.reduce(sorted_keys[128 * t:128 * t + 128]))), C.c_int32(kv))
+    return out.view(np.int32)
+
+
+def test_tile_masks_from_sorted_keys(emu):
+    c = small_cloud(17, 3000, spread=0.4, batch=0)
+    coarse, parent, code = ocd.stride2(c, 1)
+    for cols in (ocd.kmap_subm(c, 3, 1).T, ocd.kmap_down2(parent, code, coarse.shape[0]).T, ocd.kmap_up2(parent, code).T):
+        got, rows, keys = emu_sort(emu, np.ascontiguousarray(cols))
+        np.testing.assert_array_equal(emu_tile_masks(emu, keys, cols.shape[0]), tile_masks_reference(got))
+
+
 def test_bit_order(emu):
     bits = [emu.emu_tile_sort_bit(k) for k in range(27)]
     assert bits == list(bit_order())
@@ -150,8 +178,8 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
 
     def fake_sort(nbr):
         calls.append(nbr.shape)
-        s, rows, _ = emu_sort(emu, nbr.numpy())
-        return torch.from_numpy(s), torch.from_numpy(rows)
+        s, rows, keys = emu_sort(emu, nbr.numpy())
+        return torch.from_numpy(s), torch.from_numpy(rows), torch.from_numpy(emu_tile_masks(emu, keys, nbr.shape[0]))
 
     monkeypatch.setattr(ops, "kmap_tile_sort", fake_sort)
 
@@ -167,21 +195,22 @@ def test_kernel_map_hands_out_the_sorted_table(emu, monkeypatch):
     km_1x1 = coords.KernelMap(coords.NeighbourTable(None, 1, n), n, n, None, False)
     try:
         gcdlss_b200.set_tile_sort(False)
-        assert km3.tc_table() == (km3.nbr, None) and not calls
+        assert km3.tc_table() == (km3.nbr, None, None) and not calls
         gcdlss_b200.set_tile_sort(True, min_rows=n + 1)
         assert km3.tc_table()[1] is None and not calls                      # too few rows to pay for the sort
         gcdlss_b200.set_tile_sort(True, min_rows=1)
-        table, rows = km3.tc_table()
+        table, rows, masks = km3.tc_table()
         assert rows is not None and torch.equal(table, nbr[:, rows.long()]) and len(calls) == 1
+        assert masks.tolist() == tile_masks_reference(table.numpy()).tolist()
         assert km3.tc_table()[0] is table and len(calls) == 1               # cached
         assert km3.tc_back_table()[0] is table                              # stride-1 maps are self-transposed
-        t_down, r_down = km_down.tc_table()                                 # 2x2x2 tables are sorted as well
+        t_down, r_down, _ = km_down.tc_table()                              # 2x2x2 tables are sorted as well
         assert r_down is not None and torch.equal(t_down, km_down.nbr[:, r_down.long()])
         assert km_up.tc_back_table()[0] is t_down and km_down.tc_back_table()[0] is km_up.tc_table()[0]
         t5 = coords.NeighbourTable(torch.zeros((125, n), dtype=torch.int32), 125, n)
         km5 = coords.KernelMap(t5, n, n, t5, True)
-        assert km5.tc_table() == (km5.nbr, None)                            # the 5x5x5 stem goes through im2col: not sorted
-        assert km_1x1.tc_table() == (None, None) and km_1x1.tc_back_table() == (None, None)
+        assert km5.tc_table() == (km5.nbr, None, None)                      # the 5x5x5 stem goes through im2col: not sorted
+        assert km_1x1.tc_table() == (None, None, None) and km_1x1.tc_back_table() == (None, None, None)
     finally:
         gcdlss_b200.set_tile_sort(prev[0], min_rows=prev[1])
 

@@ -10,11 +10,11 @@ import torch
 from conftest import small_cloud
 from oracle import conv as oc
 from oracle import coords as ocd
-from test_tile_sort_model import emu, emu_sort  # noqa: F401  (emu is a fixture)
+from test_tile_sort_model import emu, emu_sort, emu_tile_masks  # noqa: F401  (emu is a fixture)
 
 
 def fake_conv_forward(inp, nbr, w3, n_out, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=0, w_packed=None,
-                      stats=None, out_rows=None):
+                      stats=None, out_rows=None, tile_masks=None):
     """gcd_conv_forward's contract in torch (fp64 accumulation)."""
     kv = w3.shape[0]
     x = inp.double()
@@ -40,8 +40,8 @@ def patched(emu, monkeypatch):  # noqa: F811
         return fake_conv_forward(*a, **kw)
 
     def tile_sort(nbr):
-        s, rows, _ = emu_sort(emu, nbr.numpy())
-        return torch.from_numpy(s), torch.from_numpy(rows)
+        s, rows, keys = emu_sort(emu, nbr.numpy())
+        return torch.from_numpy(s), torch.from_numpy(rows), torch.from_numpy(emu_tile_masks(emu, keys, nbr.shape[0]))
 
     monkeypatch.setattr(ops, "conv_forward", conv_forward)
     monkeypatch.setattr(ops, "kmap_tile_sort", tile_sort)
@@ -105,17 +105,18 @@ def test_fill_unit_points_at_the_sorted_tables(patched, monkeypatch):
     w = torch.zeros(27, 16, 32)
     u = ConvBnUnit()
     functional._fill_unit(u, w, bn.weight, bn.bias, bn, km3, Holder, True, True)
-    table, rows = km3.tc_table()
-    assert (u.nbr, u.out_rows) == (table.data_ptr(), rows.data_ptr())
-    assert (u.back_nbr, u.back_out_rows, u.back_mirror) == (table.data_ptr(), rows.data_ptr(), 1)
+    table, rows, masks = km3.tc_table()
+    assert (u.nbr, u.out_rows, u.tile_masks) == (table.data_ptr(), rows.data_ptr(), masks.data_ptr())
+    assert (u.back_nbr, u.back_out_rows, u.back_tile_masks, u.back_mirror) == (table.data_ptr(), rows.data_ptr(), masks.data_ptr(), 1)
     assert u.pair_in == km3.pairs[0].data_ptr() and u.n_pairs == km3.pairs[0].shape[0]      # pair lists of the ORIGINAL table
     Holder._pk_mirror = False
     u = ConvBnUnit()
     functional._fill_unit(u, torch.zeros(8, 16, 32), bn.weight, bn.bias, bn, km_down, Holder, True, True)
-    t_down, r_down = km_down.tc_table()
-    t_up, r_up = km_up.tc_table()
+    t_down, r_down, m_down = km_down.tc_table()
+    t_up, r_up, m_up = km_up.tc_table()
     assert (u.nbr, u.out_rows, u.back_nbr, u.back_out_rows) == (t_down.data_ptr(), r_down.data_ptr(), t_up.data_ptr(), r_up.data_ptr())
+    assert (u.tile_masks, u.back_tile_masks) == (m_down.data_ptr(), m_up.data_ptr())
     # SIMT units (tc False) keep the scan-order table and no row map
     u = ConvBnUnit()
     functional._fill_unit(u, w, bn.weight, bn.bias, bn, km3, Holder, False, True)
-    assert (u.nbr, u.out_rows, u.back_out_rows) == (km3.nbr.data_ptr(), None, None)
+    assert (u.nbr, u.out_rows, u.back_out_rows, u.tile_masks) == (km3.nbr.data_ptr(), None, None, None)

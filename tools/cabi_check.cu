@@ -155,8 +155,8 @@ int main() {
   {
     const size_t ws_bytes = gcd_tile_sort_workspace_bytes(n);
     void* ws; CK(cudaMalloc(&ws, ws_bytes));
-    GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, ws, ws_bytes, nullptr));
-    const float t = time_ms([&] { GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, ws, ws_bytes, nullptr)); });
+    GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, nullptr, ws, ws_bytes, nullptr));
+    const float t = time_ms([&] { GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, nullptr, ws, ws_bytes, nullptr)); });
     rows = download(d_rows, n);
     std::vector<int32_t> sorted = download(d_sorted, (size_t)kv * n);
     std::vector<uint64_t> key(n, 0);

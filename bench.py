@@ -28,11 +28,12 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (scan kind, scans per GPU, points per scan (None = full sweep), classes)
-    "kitti_b4": ("kitti", 4, None, 17),          # BASELINE.json configs[1]
-    "nuscenes_b16": ("nuscenes", 16, None, 14),  # configs[2]
+    # name: (scan kind, scans per GPU, points per scan (None = full sweep), classes, step)
+    "kitti_b4": ("kitti", 4, None, 17, "stage1"),          # BASELINE.json configs[1]: the headline line
+    "nuscenes_b16": ("nuscenes", 16, None, 14, "stage1"),  # configs[2]
+    "stage2": ("kitti", 4, None, 17, "stage2"),            # configs[3]: mean-teacher step, 2 labelled + 2 unlabelled scans per GPU
+    "dense": ("dense", 1, None, 17, "stage1"),             # configs[4]: one ~1.2 M-point aggregated scan per GPU (hashing / kernel-map stress)
 }
-# configs[3] (Stage-2 mean-teacher step) is exercised by tests/test_gpu_stage2.py and tools/bench_stage2.py
 METRIC = "MinkUNet fwd+bwd scans/sec"
 
 
@@ -106,7 +107,7 @@ def make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches)
         scans = []
         for s in range(scans_per_gpu):
             idx = scan_index(rank, b, s, n_batches, scans_per_gpu)
-            xyz, feat = synth.make_scan(kind, idx, n_points=n_points)
+            xyz, feat = synth.make_dense_scan(idx) if kind == "dense" else synth.make_scan(kind, idx, n_points=n_points)
             pts = torch.from_numpy(np.concatenate([xyz, feat], 1)).pin_memory()
             lab = torch.from_numpy(np.random.default_rng(idx).integers(0, n_classes, xyz.shape[0])).pin_memory()
             scans.append((pts, lab))
@@ -233,17 +234,41 @@ def run_ours(args):
     path_cfg = {"tile_sort": {"enabled": bool(gcfg.get_tile_sort() and args.dtype == "bf16"), "min_rows": gcfg.tile_sort_min_rows()},
                 "kmap_search": gcfg.get_kmap_search()}
 
+    stage = WORKLOADS[args.workload][4]
     torch.manual_seed(1234)
-    model = MinkUNetBase(num_classes=n_classes).to(dev).train()
+    if stage == "stage2":
+        # Stage-2 model pair (ref modules/exp_merge_mean_teacher.py:95-160): MinkUNet34RC student + EMA teacher with the
+        # novel-class heads bolted on by the Lightning module
+        import copy
+        from gcdlss_b200.steps import Stage2Harness, make_stage2_half
+        from models.multiheadminkunet import MinkUNetRC
+        model = MinkUNetRC(n_classes).to(dev).train()
+        for name, n_out in (("final2", 3), ("final3", 2)):
+            setattr(model.encoder, name, ME.MinkowskiConvolution(96, n_out, kernel_size=1, bias=True, dimension=3).to(dev))
+        teacher = copy.deepcopy(model)
+    else:
+        model = MinkUNetBase(num_classes=n_classes).to(dev).train()
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, fused=True)     # ref modules/exp.py:155-174
     reducer = GradBucketReducer(model.parameters()) if world > 1 else None
+    if reducer is not None:
+        reducer.broadcast_buffers(model)
 
     n_batches = 3
     host_batches = make_host_batches(kind, scans_per_gpu, n_points, n_classes, rank, n_batches)
-    resident = [quantize_batch_on_gpu(b, q, dev) for b in host_batches]
+    if stage == "stage2":
+        half = scans_per_gpu // 2
+
+        def stage2_batch(b):               # first half of the scans labelled, second half unlabelled
+            return (make_stage2_half(kind, 0, half, None, dev, True, n_classes, host_scans=b[:half]),
+                    make_stage2_half(kind, 0, scans_per_gpu - half, None, dev, False, n_classes, host_scans=b[half:]))
+        resident = [stage2_batch(b) for b in host_batches]
+        harness = Stage2Harness(model, teacher, opt, voxel_size=q, reducer=reducer)
+        voxels = int(np.mean([r[0]["coords"].shape[0] + r[1]["coords"].shape[0] for r in resident]))
+    else:
+        resident = [quantize_batch_on_gpu(b, q, dev) for b in host_batches]
+        voxels = int(np.mean([r[0].shape[0] for r in resident]))
     torch.cuda.synchronize()
     h2d_bytes = int(np.mean([sum(p.numel() * 4 + l.numel() * 8 for p, l in b) for b in host_batches]))
-    voxels = int(np.mean([r[0].shape[0] for r in resident]))
     points = int(np.mean([sum(p.shape[0] for p, _ in b) for b in host_batches]))
 
     from gcdlss_b200.prefetch import BatchPrefetcher
@@ -278,6 +303,8 @@ def run_ours(args):
         return prefetcher.submit(make)
 
     def step_resident(i):
+        if stage == "stage2":              # the harness builds its two SparseTensors (shared batch, LaserMix batch) itself
+            return harness.step(*resident[i % n_batches])
         cur = pending.pop("r", None) or prepare_resident(i)
         pending["r"] = prepare_resident(i + 1)
         st, labels = cur.get()
@@ -296,10 +323,13 @@ def run_ours(args):
             loss_log.append(float(loss_host[pending.pop("loss_slot")]))
 
     def step_e2e(i):
-        cur = pending.pop("e", None) or prepare_e2e(i)
-        pending["e"] = prepare_e2e(i + 1)
-        st, labels = cur.get()
-        loss = train_step(st, labels)
+        if stage == "stage2":              # H2D of the four scans + GPU quantisation of both halves + the step
+            loss = harness.step(*stage2_batch(host_batches[i % n_batches]))
+        else:
+            cur = pending.pop("e", None) or prepare_e2e(i)
+            pending["e"] = prepare_e2e(i + 1)
+            st, labels = cur.get()
+            loss = train_step(st, labels)
         read_pending_loss()                   # result of the previous step
         slot = i & 1
         loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
@@ -316,19 +346,51 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, finish=None):
+        """(total ms, per-step device intervals in ms): K steps between two CUDA events after a barrier + synchronize on both
+        sides (max over ranks), plus one event after every step for the step-time percentiles."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        e1 = torch.cuda.Event(enable_timing=True)
+        marks[0].record()
         for i in range(steps):
             fn(i)
+            marks[i + 1].record()
         if finish is not None:
             finish()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([marks[0].elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+
+    def warm_up(fn, finish=None):
+        """At least W steps and every batch shape twice, then windows of 2 * n_batches steps until a window is no more than
+        3 % faster than the one before it (at most 4 s): a fresh process / fresh box keeps speeding up for a second or two
+        (allocator, clocks, host caches).  All ranks take the same decision (max over ranks).  Used by BOTH timed loops."""
+        n = max(args.warmup, 2 * n_batches + 2)
+        for i in range(n):
+            fn(i)
+        prev, spent = None, 0.0
+        fixed = bool(os.environ.get("GCDLSS_BENCH_FIXED_WARMUP"))   # profiling runs (ncu --launch-skip needs a fixed launch count)
+        while spent < 4.0 and not fixed:                            # `spent` is built from all-reduced times: same on every rank
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(2 * n_batches):
+                fn(n + i)
+            torch.cuda.synchronize()
+            win = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(win, op=dist.ReduceOp.MAX)
+            win = float(win.item())
+            spent += win
+            n += 2 * n_batches
+            if prev is not None and win > 0.97 * prev:
+                break
+            prev = win
+        if finish is not None:
+            finish()
+        return n
 
     # The sampler (an nvidia-smi process polling every 100 ms) is started BEFORE the warm-up: its start-up (NVML / driver
     # initialisation, ~0.5 s) slows kernel launches of this process while it lasts, which used to fall exactly into the
@@ -336,29 +398,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("GCDLSS_BENCH_NO_CLOCKS"):       # (diagnosis only: the sampler is part of the contract)
         clocks.start()
-    n_warm = max(args.warmup, 2 * n_batches + 2)                # at least W; every batch shape seen twice before timing
-    for i in range(n_warm):
-        step_resident(i)
-    # A fresh process / fresh box keeps speeding up for a second or two after the first steps (allocator, clocks, host
-    # caches): keep warming in windows of 2 * n_batches steps until a window is no more than 3 % faster than the one
-    # before it (at most 4 s).  All ranks take the same decision (max over ranks).
-    prev, spent = None, 0.0
-    fixed_warmup = bool(os.environ.get("GCDLSS_BENCH_FIXED_WARMUP"))   # profiling runs (ncu --launch-skip needs a fixed launch count)
-    while spent < 4.0 and not fixed_warmup:                     # `spent` is built from all-reduced times: same on every rank
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(2 * n_batches):
-            step_resident(n_warm + i)
-        torch.cuda.synchronize()
-        win = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(win, op=dist.ReduceOp.MAX)
-        win = float(win.item())
-        spent += win
-        n_warm += 2 * n_batches
-        if prev is not None and win > 0.97 * prev:
-            break
-        prev = win
+    n_warm = warm_up(step_resident)
     import gc
     gc.collect()
     gc.freeze()            # model / maps / library objects are long-lived: keep the cyclic GC from re-walking them every few steps
@@ -384,16 +424,20 @@ def run_ours(args):
         gc.callbacks.remove(_gc_cb)
     clocks.mark()
     launches0 = ops.launch_counter["calls"]
-    total_ms = timed(step_resident, args.steps)
+    if reducer is not None:
+        reducer.measure = True
+    total_ms, step_ms = timed(step_resident, args.steps)
     launches = ops.launch_counter["calls"] - launches0
+    comm_exposed_ms = None
+    if reducer is not None:                # time the training stream spent waiting for the gradient all-reduce (per step)
+        reducer.measure = False
+        comm_exposed_ms = sum(a.elapsed_time(b) for a, b in reducer.exposed_events) / max(len(reducer.exposed_events), 1)
     if args.no_e2e:
-        e2e_ms = float("nan")
+        e2e_ms, e2e_step_ms = float("nan"), [float("nan")]
     else:
-        for i in range(max(args.warmup, 2 * n_batches + 2)):     # same rule as above: the e2e path allocates its own shapes
-            step_e2e(i)
-        finish_e2e()
+        warm_up(step_e2e, finish_e2e)          # the e2e path allocates its own shapes: same warm-up rule as above
         loss_log.clear()
-        e2e_ms = timed(step_e2e, args.steps, finish_e2e)
+        e2e_ms, e2e_step_ms = timed(step_e2e, args.steps, finish_e2e)
         assert len(loss_log) == args.steps and all(np.isfinite(loss_log)), "every timed e2e step must have delivered its loss to the host"
     clock_info = clocks.stop() if rank == 0 else None
 
@@ -408,16 +452,20 @@ def run_ours(args):
     # events; the share of the step is that kernel time over the measured step time.
     roofline = None
     # the capture step contains the gradient all-reduce, so every rank runs it; only rank 0 records and replays
+    from gcdlss_b200 import coords as gcoords
     ops.kernel_timer.captured.clear()
     ops.kernel_timer.capture = rank == 0
-    cap_st = ME.SparseTensor(features=resident[0][1], coordinates=resident[0][0])
-    train_step(cap_st, resident[0][2])
+    gcoords.TABLE_LOG = []                 # every neighbour table built during the capture step (one or two coordinate managers)
+    if stage == "stage2":
+        harness.step(*resident[0])
+    else:
+        train_step(ME.SparseTensor(features=resident[0][1], coordinates=resident[0][0]), resident[0][2])
     ops.kernel_timer.capture = False
+    tables, gcoords.TABLE_LOG = gcoords.TABLE_LOG, None
     torch.cuda.synchronize()
     if rank == 0:
-        mgr = cap_st.coordinate_manager
         pair_count = {}
-        for table in mgr._tables.values():               # every pointer a convolution launch may carry -> pairs of that table
+        for table in tables:                             # every pointer a convolution launch may carry -> pairs of that table
             if table.nbr is not None:
                 n_pairs = int(table.pairs[2][-1].item())
                 for t in table.device_tensors():
@@ -470,17 +518,27 @@ def run_ours(args):
         cpu_baseline = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port",
                         "sample": f"1 warm-up + {n_timed} timed {kind}-like scans, one per step (quantise + MinkUNet34C fwd + CE + bwd) through the CPU oracle, torch CPU fp32, {cores} threads"}
 
+    def pct(v):
+        return {"p10": float(np.percentile(v, 10)), "p50": float(np.percentile(v, 50)), "p90": float(np.percentile(v, 90))}
+
+    descr = {"stage1": ("MinkUNet34RC backbone + final head (Stage-1 MinkUNetBase, ref modules/exp.py:249-267)",
+                        "hash + kernel maps (side stream, one batch ahead) + fwd + CE + bwd + grad all-reduce + SGD"),
+             "stage2": ("MinkUNet34RC student + EMA teacher with final/final2/final3 heads (ref modules/exp_merge_mean_teacher.py:2772-2875)",
+                        "teacher fwd + student fwd on the shared 4-scan batch, CE + 200 MSE, pseudo labels -> points, LaserMix, GPU quantise, "
+                        "student fwd on the mixed batch, bwd through both, grad all-reduce, SGD, EMA")}[stage]
     if rank == 0:
+        total_gflop = sum(v["flops"] for v in classes.values()) / 1e9 if roofline else None
         line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": n_warm,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "scans_per_gpu": scans_per_gpu, "points_per_batch": points, "voxels_per_batch": voxels,
-                           "model": "MinkUNet34RC backbone + final head (Stage-1 MinkUNetBase)", "classes": n_classes,
-                           "step": "hash + kernel maps (side stream, one batch ahead) + fwd + CE + bwd + grad all-reduce + SGD", "parallelism": f"dp{world}",
+                           "voxels_per_s": voxels * world * args.steps / (total_ms / 1e3), "conv_gflop_per_step_per_gpu": total_gflop,
+                           "model": descr[0], "classes": n_classes, "step": descr[1], "parallelism": f"dp{world}",
                            "l2": f"{n_batches} distinct batches rotate; per-step activations + maps exceed the 126 MB L2",
                            **path_cfg},
                 "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + 8 * scans_per_gpu,
-                        "ms_per_step": e2e_ms / args.steps},
+                        "ms_per_step": e2e_ms / args.steps, "step_ms": pct(e2e_step_ms)},
+                "step_ms": pct(step_ms), "comm_exposed_ms_per_step": comm_exposed_ms,
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info,
                 "grad_allreduce_bytes": reducer.grad_bytes() if reducer is not None else 0}
         print(json.dumps(line), flush=True)

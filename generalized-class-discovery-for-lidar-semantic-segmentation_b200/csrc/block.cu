@@ -48,6 +48,55 @@ int32_t add_inplace(void* dst, const void* src, int64_t n, int32_t c, int32_t dt
   return GCD_OK;
 }
 
+// dst[i, 0:c] (=|+=) src[i, 0:c] in 16-byte vectors; `vpr` vectors per row.
+template <typename T, bool kAdd>
+__global__ void cols_kernel(T* __restrict__ dst, int64_t ld_dst, const T* __restrict__ src, int64_t ld_src, int64_t n, int vpr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * vpr) return;
+  const int64_t row = t / vpr;
+  const int v = (int)(t - row * vpr);
+  constexpr int per = 16 / (int)sizeof(T);
+  const uint4 b = *reinterpret_cast<const uint4*>(src + row * ld_src + (int64_t)v * per);
+  uint4* d = reinterpret_cast<uint4*>(dst + row * ld_dst + (int64_t)v * per);
+  if constexpr (!kAdd) { *d = b; return; }
+  uint4 a = *d;
+  if constexpr (sizeof(T) == 4) {
+    float* fa = reinterpret_cast<float*>(&a);
+    const float* fb = reinterpret_cast<const float*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fa[j] += fb[j];
+  } else {
+    __nv_bfloat162* ha = reinterpret_cast<__nv_bfloat162*>(&a);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = __bfloat1622float2(ha[j]), y = __bfloat1622float2(hb[j]);
+      ha[j] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+    }
+  }
+  *d = a;
+}
+
+int32_t cols_op(const gcd_op* o, bool add, cudaStream_t st) {
+  if (o->n == 0 || o->c == 0) return GCD_OK;
+  const int esz = o->dtype == GCD_F32 ? 4 : 2, per = 16 / esz;
+  GCD_REQUIRE(o->dst && o->src && o->n > 0 && o->c > 0, "gcd_run_ops: bad copy / add operands");
+  GCD_REQUIRE(o->c % per == 0 && o->ld_dst % per == 0 && o->ld_src % per == 0 && o->ld_dst >= o->c && o->ld_src >= o->c &&
+              (reinterpret_cast<uintptr_t>(o->dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(o->src) & 15) == 0,
+              "gcd_run_ops: column copies need 16-byte aligned rows (c = %d)", o->c);
+  const int vpr = o->c / per;
+  const unsigned g = (unsigned)ceil_div(o->n * vpr, 256);
+  if (o->dtype == GCD_F32) {
+    if (add) cols_kernel<float, true><<<g, 256, 0, st>>>((float*)o->dst, o->ld_dst, (const float*)o->src, o->ld_src, o->n, vpr);
+    else cols_kernel<float, false><<<g, 256, 0, st>>>((float*)o->dst, o->ld_dst, (const float*)o->src, o->ld_src, o->n, vpr);
+  } else {
+    if (add) cols_kernel<__nv_bfloat16, true><<<g, 256, 0, st>>>((__nv_bfloat16*)o->dst, o->ld_dst, (const __nv_bfloat16*)o->src, o->ld_src, o->n, vpr);
+    else cols_kernel<__nv_bfloat16, false><<<g, 256, 0, st>>>((__nv_bfloat16*)o->dst, o->ld_dst, (const __nv_bfloat16*)o->src, o->ld_src, o->n, vpr);
+  }
+  GCD_LAUNCH_CHECK("gcd_run_ops(copy/add)");
+  return GCD_OK;
+}
+
 #define GCD_TRY(expr)                 \
   do {                                \
     int32_t rc__ = (expr);            \
@@ -101,11 +150,12 @@ int32_t unit_bn_fwd(const gcd_convbn* u, const void* x, const void* res, int32_t
                             u->running_var, u->mean, u->invstd, res, res ? u->c_out : 0, relu, y, u->c_out, dtype, stream);
 }
 
-int32_t unit_bn_bwd(const gcd_convbn* u, const void* dy, const void* x, const void* y, int32_t relu, void* dx, void* dres,
+int32_t unit_bn_bwd(const gcd_convbn* u, const void* dy, int64_t ld_dy, const void* x, const void* y, int32_t relu, void* dx, void* dres,
                     int32_t dtype, void* stream) {
   const int64_t ld = u->c_out;
-  GCD_TRY(gcd_bn_backward_reduce(dy, ld, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, relu, dtype, u->sums, stream));
-  return gcd_bn_backward_apply(dy, ld, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, u->gamma, u->sums, relu, 1, dx, ld,
+  if (ld_dy == 0) ld_dy = ld;
+  GCD_TRY(gcd_bn_backward_reduce(dy, ld_dy, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, relu, dtype, u->sums, stream));
+  return gcd_bn_backward_apply(dy, ld_dy, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, u->gamma, u->sums, relu, 1, dx, ld,
                                dres, dres ? ld : 0, u->dgamma, u->dbeta, dtype, stream);
 }
 
@@ -166,23 +216,25 @@ extern "C" int32_t gcd_block_backward(gcd_block_args* b, void* stream) {
   b->launches = 0;
   if (b->u1.n_out == 0) return GCD_OK;
   const void* g1 = b->gout;       // gradient arriving at the first unit's activation
+  int64_t ld_g1 = b->ld_gout;
   if (b->has_u2) {
     GCD_REQUIRE(b->dy2 && b->dres && b->da1 && b->u2.sums && b->u2.dw && b->u2.dgamma && b->u2.dbeta, "gcd_block_backward: null pointer (u2)");
-    GCD_TRY(unit_bn_bwd(&b->u2, b->gout, b->y2, b->out, 1, b->dy2, b->dres, dt, stream));
+    GCD_TRY(unit_bn_bwd(&b->u2, b->gout, b->ld_gout, b->y2, b->out, 1, b->dy2, b->dres, dt, stream));
     GCD_TRY(unit_dgrad(&b->u2, b->dy2, b->da1, dt, stream));
     GCD_TRY(unit_wgrad(&b->u2, b->a1, b->u1.c_out, b->dy2, dt, stream));
     g1 = b->da1;
+    ld_g1 = 0;
     n += 4;
   }
   const int32_t relu1 = b->has_u2 ? 1 : b->relu1;
-  GCD_TRY(unit_bn_bwd(&b->u1, g1, b->y1, relu1 ? b->a1 : nullptr, relu1, b->dy1, nullptr, dt, stream));
+  GCD_TRY(unit_bn_bwd(&b->u1, g1, ld_g1, b->y1, relu1 ? b->a1 : nullptr, relu1, b->dy1, nullptr, dt, stream));
   if (b->need_dx) { GCD_TRY(unit_dgrad(&b->u1, b->dy1, b->dx, dt, stream)); ++n; }
   GCD_TRY(unit_wgrad(&b->u1, b->x, b->ld_x, b->dy1, dt, stream));
   n += 3;
   if (b->has_u2) {
     if (b->has_ud) {
       GCD_REQUIRE(b->dyd && b->ud.sums && b->ud.dw && b->ud.dgamma && b->ud.dbeta, "gcd_block_backward: null pointer (ud)");
-      GCD_TRY(unit_bn_bwd(&b->ud, b->dres, b->yd, nullptr, 0, b->dyd, nullptr, dt, stream));
+      GCD_TRY(unit_bn_bwd(&b->ud, b->dres, 0, b->yd, nullptr, 0, b->dyd, nullptr, dt, stream));
       n += 2;
       if (b->need_dx) {
         GCD_REQUIRE(b->dxd, "gcd_block_backward: null dxd");
@@ -198,5 +250,38 @@ extern "C" int32_t gcd_block_backward(gcd_block_args* b, void* stream) {
     }
   }
   b->launches = n;
+  return GCD_OK;
+}
+
+extern "C" int32_t gcd_run_ops(gcd_op* ops, int32_t n_ops, void* stream, int32_t* launches) {
+  GCD_REQUIRE(ops != nullptr && n_ops >= 0, "gcd_run_ops: bad arguments");
+  int32_t total = 0;
+  for (int32_t i = 0; i < n_ops; ++i) {
+    gcd_op* o = &ops[i];
+    switch (o->op) {
+      case GCD_OP_BLOCK_FORWARD:
+        GCD_REQUIRE(o->block != nullptr, "gcd_run_ops: operation %d has no block", i);
+        GCD_TRY(gcd_block_forward(o->block, stream));
+        total += o->block->launches;
+        break;
+      case GCD_OP_BLOCK_BACKWARD:
+        GCD_REQUIRE(o->block != nullptr, "gcd_run_ops: operation %d has no block", i);
+        GCD_TRY(gcd_block_backward(o->block, stream));
+        total += o->block->launches;
+        break;
+      case GCD_OP_COPY_COLS:
+        GCD_TRY(cols_op(o, false, as_stream(stream)));
+        ++total;
+        break;
+      case GCD_OP_ADD_COLS:
+        GCD_TRY(cols_op(o, true, as_stream(stream)));
+        ++total;
+        break;
+      default:
+        set_error("gcd_run_ops: unknown operation %d at index %d", o->op, i);
+        return GCD_ERR_INVALID_ARG;
+    }
+  }
+  if (launches) *launches = total;
   return GCD_OK;
 }

@@ -43,7 +43,10 @@ constexpr int kTableWarp = kProducerWarps + 5;        // 13 (forward kernel: sta
 constexpr int kTcThreads = kProducerThreads + kEpilogueThreads + 64;
 constexpr int kMaxKV = 27;
 constexpr int kMaxStages = 8;
-constexpr int kTileRing = 16;
+constexpr int kTileRing = 32;               // published iteration counts (the MMA warp lags the table warp by < kTableSlots + kMaxStages tiles)
+constexpr int kSliceBytes = kTileM * 4;     // one offset's [128] slice of the neighbour table
+constexpr int kRingSlices = 56;             // shared-memory ring of table slices: two whole 3x3x3 tiles, ~6 tiles of a sorted table
+constexpr int kTableSlots = 8;              // tiles the table warp may run ahead (barriers / masks per slot)
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM columns between the two accumulator buffers
 constexpr int kSmemBudget = 226 * 1024;
@@ -77,8 +80,8 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
   L.a_off = 0;
   L.b_off = L.a_off + (uint32_t)stages * kABytes;
   L.nbr_off = L.b_off + (uint32_t)stages * L.b_bytes;
-  L.bar_off = L.nbr_off + 2 * kMaxKV * kTileM * 4;     // two table buffers (tile t and t + 1)
-  L.total = L.bar_off + 512;
+  L.bar_off = L.nbr_off + kRingSlices * kSliceBytes;   // ring of table slices
+  L.total = L.bar_off + 1024;
   return L;
 }
 
@@ -86,23 +89,27 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
 // With kNQ known the slice loop is unrolled and every copy uses an immediate offset from a per-offset base
 // pointer, which is what keeps the producer loop at a few dozen instructions per stage.
 // kPerm (tile-sorted tables, tilesort.cu): table column i is output row p.out_rows[i]; only the epilogue's store address changes.
-template <int kNQ, bool kPerm = false>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdParams p) {
+// kPW = gather warps (8, or 16: two warps per ring slot; the gather is issue-bound per warp at ~90 cycles per warp-level copy,
+// the LSU takes one every ~8): warps [0, kPW) gather, [kPW, kPW + 4) epilogue, kPW + 4 MMA, kPW + 5 table.
+template <int kNQ, bool kPerm = false, int kPW = kProducerWarps>
+__global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const FwdParams p) {
+  constexpr int kEpi0 = kPW, kMma = kPW + 4, kTab = kPW + 5;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is at least 16-byte aligned; the swizzle pattern needs 1024.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const SmemLayout L = make_layout(p.stages, p.n_tile_cols);
-  int32_t* s_nbr0 = reinterpret_cast<int32_t*>(smem + L.nbr_off);           // [2][kv][128]
+  int32_t* s_nbr0 = reinterpret_cast<int32_t*>(smem + L.nbr_off);           // [kRingSlices][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* full_bar = bars;                    // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;      // [kMaxStages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint64_t* table_ready = tmem_empty + 2;       // [2] table buffer b holds the complete slice of its tile (table warp -> producers)
-  uint64_t* table_free = table_ready + 2;       // [2] every producer warp is done reading buffer b
-  uint32_t* s_tmem_base = reinterpret_cast<uint32_t*>(table_free + 2);
-  uint32_t* s_mask = s_tmem_base + 1;           // [2] offsets with at least one hit in the tile of buffer b
-  int32_t* s_iters = reinterpret_cast<int32_t*>(s_mask + 2);  // [kTileRing]
+  uint64_t* table_ready = tmem_empty + 2;       // [kTableSlots] the slices of the slot's tile have landed (table warp -> producers)
+  uint64_t* table_free = table_ready + kTableSlots;   // [kTableSlots] every producer warp is done with the slot's tile
+  uint32_t* s_tmem_base = reinterpret_cast<uint32_t*>(table_free + kTableSlots);
+  uint32_t* s_mask = s_tmem_base + 1;           // [kTableSlots] offsets with at least one hit in the slot's tile
+  uint32_t* s_base = s_mask + kTableSlots;      // [kTableSlots] ring position of the tile's first slice, bit 31: slices are compacted (mask order)
+  int32_t* s_iters = reinterpret_cast<int32_t*>(s_base + kTableSlots);  // [kTileRing]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -116,10 +123,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     // full: one completion-triggered arrival per lane of the owning producer warp + its lane 0's arrive.expect_tx (weights)
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 32 * p.group + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&table_ready[b], 1); mbar_init(&table_free[b], kProducerWarps); }
+    // ready: one completion-triggered arrival per lane of the table warp (its cp.async copies) + lane 0's plain arrive
+    for (int b = 0; b < kTableSlots; ++b) { mbar_init(&table_ready[b], 33); mbar_init(&table_free[b], kPW); }
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
+  if (warp == kMma) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     if (hi == 0) { hi = lo; lo = 0; }
   };
 
-  if (warp < kProducerWarps) {
+  if (warp < kPW) {
     // ===================================================================== gather producers (stage owners)
     // Producer warp (or warp pair) w OWNS the stages of iterations g == w (mod PA), PA = min(8 / G, stages): it waits for the slot, posts
     // the weight slice (one bulk copy on the TMA engine) and gathers all 128 rows x 64 channels itself (32 cp.async per
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
     // stay busy and a stage is issued in half the time; otherwise one warp per stage.
     const int G = p.group;                     // warps per stage: 1, 2, 4 or 8
     const int grp = warp / G, sub = warp % G;
-    const int PA = (kProducerWarps / G) < S ? (kProducerWarps / G) : S;   // owner groups (<= stages: a waiter may be one phase behind at most)
+    const int PA = (kPW / G) < S ? (kPW / G) : S;   // owner groups (<= stages: a waiter may be one phase behind at most)
     const uint32_t lane0 = (lane == 0 && sub == 0) ? 1u : 0u;
 
     uint32_t st = grp, ph = 0;                 // stage / parity of this group's next owned iteration
@@ -170,10 +178,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #endif
       // the table warp stages the slice one tile ahead: no producer-wide synchronisation at tile boundaries, a warp
       // that has issued its last stage of tile t goes straight on to its first stage of tile t + 1
-      const uint32_t tb = tile_seq & 1;
-      mbar_wait(&table_ready[tb], (tile_seq >> 1) & 1);
-      const uint32_t s_nbr_addr = smem_u32(s_nbr0) + tb * (uint32_t)(kMaxKV * kTileM * 4);
-      uint32_t mask = s_mask[tb], lo_mask;
+      const uint32_t tb = tile_seq % kTableSlots;
+      mbar_wait(&table_ready[tb], (tile_seq / kTableSlots) & 1);
+      const uint32_t s_nbr_addr = smem_u32(s_nbr0);
+      const uint32_t tile_mask = s_mask[tb], tile_base = s_base[tb] & 0x7fffffffu;
+      const bool compact = (s_base[tb] >> 31) != 0;
+      uint32_t mask = tile_mask, lo_mask;
       rotate(mask, mask, lo_mask);
       const uint8_t* w_tile = p.w_packed + (int64_t)(work % p.n_tiles_n) * p.n_tile_cols * kRowBytes;
 #ifdef GCD_TC_PROFILE
@@ -206,7 +216,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
           if (!(p.ablate & 2))
 #endif
           if (q + 1 < nq || last_active) {
-            const uint32_t nb = s_nbr_addr + (uint32_t)(k * kTileM + rsub) * 4u;
+            // ring position of offset k's slice: compacted tiles hold their slices in mask order
+            uint32_t pos = tile_base + (compact ? (uint32_t)__popc(tile_mask & ((1u << k) - 1u)) : (uint32_t)k);
+            if (pos >= (uint32_t)kRingSlices) pos -= kRingSlices;
+            const uint32_t nb = s_nbr_addr + (pos * kTileM + (uint32_t)rsub) * 4u;
             const uint32_t a_stage = a_base + st * kABytes;
             const char* src_q = col_base + q * (kChunkK * 2);
 #pragma unroll
@@ -233,85 +246,110 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #ifdef GCD_TC_PROFILE
     if (p.dbg && threadIdx.x == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[0] = clock64() - prof_t0; d[1] = prof_table; d[2] = prof_wait; d[3] = prof_iters; d[7] = tile_seq; }
 #endif
-  } else if (warp == kTableWarp) {
+  } else if (warp == kTab) {
     // ===================================================================== table warp
-    // Stages the [kv][128] slice of the neighbour table of tile t + 1 while tile t is being processed (two buffers), works
-    // out which offsets have a hit in the tile and publishes the tile's iteration count for the MMA warp.
-    uint32_t tile_seq = 0;
+    // Streams neighbour-table slices ([128] int32 per kernel offset) into a shared-memory ring, as many tiles ahead of the
+    // gather warps as the ring holds (kRingSlices slices, kTableSlots tiles).  With per-tile offset masks (tile_masks) only
+    // the slices a tile uses are fetched, by cp.async straight into the ring: the warp never waits for a load, and the
+    // tile is published by completion-triggered mbarrier arrivals.  Without masks the whole [kv][128] slice goes through
+    // registers (the mask of offsets with a hit is derived on the way).  It also publishes each tile's iteration count
+    // for the MMA warp.
+    uint32_t tile_seq = 0, head = 0, used = 0, tail_seq = 0;
+    unsigned long long counts = 0;                         // slices held by the tile of each slot, 6 bits per slot
+    const uint32_t ring_addr = smem_u32(s_nbr0);
+    const bool compact = p.tile_masks != nullptr;
+    const bool aligned = (p.n_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0;
+    uint32_t next_mask = 0;
+    if (compact && (int64_t)blockIdx.x < n_work) next_mask = __ldg(&p.tile_masks[blockIdx.x / p.n_tiles_n]);
 #ifdef GCD_TC_PROFILE
     long long prof_twait = 0; const long long prof_t0 = clock64();
 #endif
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
-      const uint32_t tb = tile_seq & 1;
+      const uint32_t tb = tile_seq % kTableSlots;
+      const int64_t row0 = (work / p.n_tiles_n) * kTileM;
+      uint32_t mask = next_mask;
+      if (compact && work + gridDim.x < n_work) next_mask = __ldg(&p.tile_masks[(work + gridDim.x) / p.n_tiles_n]);   // one tile ahead
+      const uint32_t load_mask = mask ? mask : 1u;         // degenerate tile: offset 0 runs with all-zero rows
+      const uint32_t n_sl = compact ? (uint32_t)__popc(load_mask) : (uint32_t)p.kv;
 #ifdef GCD_TC_PROFILE
       const long long ctw0 = clock64();
 #endif
-      if (tile_seq >= 2) mbar_wait(&table_free[tb], ((tile_seq - 2) >> 1) & 1);
+      // room in the ring and a free slot: release the oldest tiles the gather warps are done with
+      while (used + n_sl > (uint32_t)kRingSlices || tile_seq - tail_seq >= (uint32_t)kTableSlots) {
+        const uint32_t ts = tail_seq % kTableSlots;
+        mbar_wait(&table_free[ts], (tail_seq / kTableSlots) & 1);
+        used -= (uint32_t)(counts >> (6 * ts)) & 63u;
+        ++tail_seq;
+      }
 #ifdef GCD_TC_PROFILE
       prof_twait += clock64() - ctw0;
 #endif
-      int32_t* dst = s_nbr0 + tb * (kMaxKV * kTileM);
-      const int64_t r0 = (work / p.n_tiles_n) * kTileM + lane;
-      uint32_t mask = 0;
-      if (p.tile_masks) {
-        // The tile's offsets are known (a tile of a sorted table uses 8-11 of 27, 1-3 of 8): stage only their slices, in
-        // one round of loads in most tiles instead of two rounds over the whole table slice.
-        mask = __ldg(&p.tile_masks[work / p.n_tiles_n]);
-        uint32_t todo = mask ? mask : 1u;                 // degenerate tile: offset 0 runs with all-zero rows
+      const uint32_t base = head;
+      if (compact) {
+        const bool vec = aligned && row0 + kTileM <= p.n_out;
+        uint32_t todo = load_mask, pos = base;
         while (todo) {
-          int ks[14], v[14][4];
-#pragma unroll
-          for (int kk = 0; kk < 14; ++kk) {
-            ks[kk] = todo ? __ffs(todo) - 1 : -1;
-            todo &= todo - 1;                             // 0 & 0xffffffff stays 0
+          const int k = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int32_t* src = p.nbr + (int64_t)k * p.n_out + row0;
+          const uint32_t dst = ring_addr + pos * (uint32_t)kSliceBytes;
+          if (vec) {
+            cp_async_16(dst + lane * 16, src + lane * 4, 16u);
+          } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int64_t r = r0 + 32 * j;
+              const int r = lane + 32 * j;
+              if (row0 + r < p.n_out) cp_async_4(dst + r * 4, src + r);
+              else s_nbr0[pos * kTileM + r] = -1;
+            }
+          }
+          if (++pos == (uint32_t)kRingSlices) pos = 0;
+        }
+      } else {
+        mask = 0;
+        for (int kb = 0; kb < p.kv; kb += 14) {             // 56 loads in flight per lane (a load per k would cost a memory latency each)
+          int v[14][4];
+#pragma unroll
+          for (int kk = 0; kk < 14; ++kk) {
+            const int k = kb + kk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int64_t r = row0 + lane + 32 * j;
               v[kk][j] = -1;
-              if (ks[kk] >= 0 && r < p.n_out) v[kk][j] = __ldg(&p.nbr[(int64_t)ks[kk] * p.n_out + r]);
+              if (k < p.kv && r < p.n_out) v[kk][j] = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.n_out + r]) : (int)r;
             }
           }
 #pragma unroll
-          for (int kk = 0; kk < 14; ++kk)
-            if (ks[kk] >= 0) {
+          for (int kk = 0; kk < 14; ++kk) {
+            const int k = kb + kk;
+            if (k < p.kv) {
+              uint32_t pos = base + (uint32_t)k;
+              if (pos >= (uint32_t)kRingSlices) pos -= kRingSlices;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dst[ks[kk] * kTileM + lane + 32 * j] = v[kk][j];
+              for (int j = 0; j < 4; ++j) s_nbr0[pos * kTileM + lane + 32 * j] = v[kk][j];
+              if (__any_sync(0xffffffffu, (v[kk][0] & v[kk][1] & v[kk][2] & v[kk][3]) >= 0)) mask |= 1u << k;     // some entry is not -1
             }
-        }
-      } else
-      for (int kb = 0; kb < p.kv; kb += 14) {             // 56 loads in flight per lane (a load per k would cost a memory latency each)
-        int v[14][4];
-#pragma unroll
-        for (int kk = 0; kk < 14; ++kk) {
-          const int k = kb + kk;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t r = r0 + 32 * j;
-            v[kk][j] = -1;
-            if (k < p.kv && r < p.n_out) v[kk][j] = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.n_out + r]) : (int)r;
-          }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 14; ++kk) {
-          const int k = kb + kk;
-          if (k < p.kv) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[k * kTileM + lane + 32 * j] = v[kk][j];
-            if (__any_sync(0xffffffffu, (v[kk][0] & v[kk][1] & v[kk][2] & v[kk][3]) >= 0)) mask |= 1u << k;     // some entry is not -1
           }
         }
       }
       if (lane == 0) {
         s_mask[tb] = mask;
+        s_base[tb] = base | (compact ? 0x80000000u : 0u);
         s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
       }
       __syncwarp();
+      cp_async_mbar_arrive_noinc(&table_ready[tb]);        // each lane: arrives once its copies of this tile have landed
       mbar_arrive_pred(&table_ready[tb], lane == 0 ? 1u : 0u);
+      head = base + n_sl;
+      if (head >= (uint32_t)kRingSlices) head -= kRingSlices;
+      used += n_sl;
+      counts = (counts & ~(63ull << (6 * tb))) | ((unsigned long long)n_sl << (6 * tb));
     }
+    cp_async_wait_all();
 #ifdef GCD_TC_PROFILE
     if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[8] = clock64() - prof_t0; d[9] = prof_twait; }
 #endif
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kMma) {
     // ===================================================================== MMA issuer
     // The whole warp runs the loop with warp-uniform values (so descriptors live in uniform registers and there is
     // no divergence bookkeeping around every instruction); one elected lane issues the tcgen05 instructions.
@@ -372,9 +410,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 #ifdef GCD_TC_PROFILE
     if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[4] = clock64() - prof_t0; d[5] = prof_full; d[6] = prof_acc; }
 #endif
-  } else if (warp < kMmaWarp) {
+  } else if (warp < kMma) {
     // ===================================================================== epilogue
-    const int ew = warp - kEpilogueWarp0;      // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = warp - kEpi0;      // == warp % 4: the TMEM lane quarter this warp may read
     uint32_t tile_seq = 0;
 #ifdef GCD_TC_PROFILE
     long long prof_ewait = 0; const long long prof_t0 = clock64();
@@ -432,7 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_fwd_tc_kernel(const FwdPar
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+  if (warp == kMma) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------ weight packing
@@ -745,15 +783,15 @@ bool conv_forward_tc_supported(const gcd_conv_args* a) {
 }
 
 using FwdKernel = void (*)(const FwdParams);
-template <bool kPerm>
+template <bool kPerm, int kPW = kProducerWarps>
 FwdKernel pick_fwd_kernel(int nq) {
   switch (nq) {
-    case 1: return conv_fwd_tc_kernel<1, kPerm>;
-    case 2: return conv_fwd_tc_kernel<2, kPerm>;
-    case 3: return conv_fwd_tc_kernel<3, kPerm>;
-    case 4: return conv_fwd_tc_kernel<4, kPerm>;
-    case 6: return conv_fwd_tc_kernel<6, kPerm>;
-    default: return conv_fwd_tc_kernel<0, kPerm>;
+    case 1: return conv_fwd_tc_kernel<1, kPerm, kPW>;
+    case 2: return conv_fwd_tc_kernel<2, kPerm, kPW>;
+    case 3: return conv_fwd_tc_kernel<3, kPerm, kPW>;
+    case 4: return conv_fwd_tc_kernel<4, kPerm, kPW>;
+    case 6: return conv_fwd_tc_kernel<6, kPerm, kPW>;
+    default: return conv_fwd_tc_kernel<0, kPerm, kPW>;
   }
 }
 
@@ -768,6 +806,8 @@ static cudaError_t tc_kernels_opt_in() {
     for (int nq : {0, 1, 2, 3, 4, 6}) {
       opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<false>(nq)));
       opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<true>(nq)));
+      opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<false, 16>(nq)));
+      opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<true, 16>(nq)));
     }
     opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<1>));
     opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<2>));
@@ -799,12 +839,14 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   GCD_REQUIRE(a->out_rows == nullptr || a->nbr != nullptr, "conv_forward_tc: out_rows needs a neighbour table");
   GCD_REQUIRE(a->tile_masks == nullptr || a->nbr != nullptr, "conv_forward_tc: tile_masks needs a neighbour table");
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
-  int stages = (kSmemBudget - 1024 - 2 * kMaxKV * kTileM * 4 - 512) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - kRingSlices * kSliceBytes - 1024) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   if (const int o = option(GCD_OPT_TC_STAGES); o > 0) stages = std::max(2, std::min(stages, o));   // tuning aid
   if (stages < 2) { set_error("conv_forward_tc: not enough shared memory stages"); return GCD_ERR_UNSUPPORTED; }
   p.stages = stages;
+  const int pw = option(GCD_OPT_TC_WARPS) == 16 ? 16 : 8;
   p.group = stages <= 4 ? 2 : 1;      // measured: one warp per stage is best with >= 5 stages, a warp pair when the stages are few and fat
+  if (pw == 16) p.group *= 2;         // sixteen gather warps: a warp pair (a quad when the stages are few and fat) per slot
   if (const int g = option(GCD_OPT_TC_GROUP); g == 1 || g == 2 || g == 4 || g == 8) p.group = g;   // tuning aid
 #ifdef GCD_TC_PROFILE
   p.dbg = g_debug_buffer;
@@ -813,12 +855,13 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;
   const int nq_sel = (a->c_in + kChunkK - 1) / kChunkK;
-  const FwdKernel kernel = p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel);
+  const FwdKernel kernel = pw == 16 ? (p.out_rows ? pick_fwd_kernel<true, 16>(nq_sel) : pick_fwd_kernel<false, 16>(nq_sel))
+                                    : (p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel));
   if (const cudaError_t e = tc_kernels_opt_in(); e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcgen05 kernels)");
   if (a->c_in > 16 * kChunkK) { set_error("conv_forward_tc: more than 1024 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;
   const unsigned grid = (unsigned)std::min<int64_t>(n_work, kNumSMs);
-  kernel<<<grid, kTcThreads, smem, st>>>(p);
+  kernel<<<grid, (pw + 6) * 32, smem, st>>>(p);
   GCD_LAUNCH_CHECK("gcd_conv_forward(tcgen05)");
   return GCD_OK;
 }

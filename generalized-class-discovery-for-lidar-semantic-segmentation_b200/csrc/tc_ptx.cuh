@@ -88,6 +88,10 @@ __device__ __forceinline__ void cp_async_16_pred(uint32_t dst_smem, const void* 
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}"
                ::"r"(dst_smem), "l"(src), "r"(src_bytes), "r"(pred) : "memory");
 }
+// 4-byte cp.async (cache-all; .cg only takes 16 bytes): the table warp's copies of unaligned neighbour-table slices
+__device__ __forceinline__ void cp_async_4(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>

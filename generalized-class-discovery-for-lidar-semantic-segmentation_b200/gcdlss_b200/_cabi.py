@@ -19,7 +19,7 @@ F32, BF16 = 0, 1
 MATH_FP32_SIMT, MATH_BF16_TC = 0, 1
 ROUND_FLOOR, ROUND_HALF_EVEN = 0, 1
 DEV_KEY_RANGE, DEV_DUPLICATE, DEV_TABLE_FULL = 1, 2, 4
-OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN = range(5)
+OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN, OPT_TC_WARPS = range(6)
 
 
 def build(force: bool = False) -> str:
@@ -101,7 +101,19 @@ class BlockArgs(C.Structure):
         ("y1", C.c_void_p), ("a1", C.c_void_p), ("y2", C.c_void_p), ("yd", C.c_void_p), ("rd", C.c_void_p), ("out", C.c_void_p),
         ("gout", C.c_void_p), ("dy2", C.c_void_p), ("dres", C.c_void_p), ("da1", C.c_void_p), ("dy1", C.c_void_p),
         ("dyd", C.c_void_p), ("dx", C.c_void_p), ("dxd", C.c_void_p),
-        ("need_dx", C.c_int32), ("launches", C.c_int32),
+        ("need_dx", C.c_int32), ("launches", C.c_int32), ("ld_gout", C.c_int64),
+    ]
+
+
+OP_BLOCK_FORWARD, OP_BLOCK_BACKWARD, OP_COPY_COLS, OP_ADD_COLS = range(4)
+
+
+class Op(C.Structure):
+    """gcd_op: one entry of a gcd_run_ops program."""
+    _fields_ = [
+        ("op", C.c_int32), ("dtype", C.c_int32), ("block", C.POINTER(BlockArgs)),
+        ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("src", C.c_void_p), ("ld_src", C.c_int64),
+        ("n", C.c_int64), ("c", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -158,6 +170,7 @@ PROTOTYPES = {
     "gcd_consistency_rows": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gcd_block_forward": (_i32, [C.POINTER(BlockArgs), _vp]),
     "gcd_block_backward": (_i32, [C.POINTER(BlockArgs), _vp]),
+    "gcd_run_ops": (_i32, [C.POINTER(Op), _i32, _vp, C.POINTER(_i32)]),
     "gcd_segment_reduce": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
 }
 

@@ -12,6 +12,9 @@ import torch
 from . import config, ops
 
 
+TABLE_LOG = None      # instrumentation (bench.py): when a list, every NeighbourTable built is appended to it
+
+
 class CoordMap:
     __slots__ = ("coords", "n", "table", "runs", "tensor_stride", "parent", "code")
 
@@ -165,6 +168,8 @@ class CoordinateManager:
         if t is None:
             nbr, kv, n_out = build()
             t = self._tables[key] = NeighbourTable(nbr, kv, n_out)
+            if TABLE_LOG is not None:
+                TABLE_LOG.append(t)
         return t
 
     def kernel_map(self, ts_in: int, kernel_size: int, stride: int, transposed: bool) -> KernelMap:

@@ -24,6 +24,10 @@ class GradBucketReducer:
             with torch.no_grad():
                 for p in self.params:
                     dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+        # NCCL averages in the collective itself (ReduceOp.AVG): no separate divide pass over the 151 MB of gradients
+        self._avg = self.world > 1 and dist.get_backend(process_group) == "nccl"
+        self.measure = False         # bench.py: CUDA events around the wait in finish() -> exposed communication time
+        self.exposed_events = []
         self.buckets = []            # (flat tensor, [params])
         self._owner = {}
         self._pending = []
@@ -63,7 +67,11 @@ class GradBucketReducer:
         b = self._owner[p]
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.world > 1:
-            self._handles.append(dist.all_reduce(self.buckets[b][0], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._handles.append(self._launch(b))
+
+    def _launch(self, b):
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        return dist.all_reduce(self.buckets[b][0], op=op, group=self.group, async_op=True)
 
     def broadcast_buffers(self, module):
         """Rank 0's buffers (BN running statistics) to every rank; call once after construction."""
@@ -88,11 +96,18 @@ class GradBucketReducer:
         if self.world > 1:
             for b, left in enumerate(self._pending):       # parameters that received no gradient this step
                 if left > 0:
-                    self._handles.append(dist.all_reduce(self.buckets[b][0], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                    self._handles.append(self._launch(b))
+            if self.measure:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             for h in self._handles:
                 h.wait()
-            for flat, _ in self.buckets:
-                flat.div_(self.world)
+            if not self._avg:
+                for flat, _ in self.buckets:
+                    flat.div_(self.world)
+            if self.measure:
+                e1.record()
+                self.exposed_events.append((e0, e1))
         self._handles = []
 
     def grad_bytes(self) -> int:

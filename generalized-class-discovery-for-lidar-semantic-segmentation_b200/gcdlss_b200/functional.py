@@ -464,3 +464,318 @@ def voxelize_reduce(point_feats: torch.Tensor, inverse_map: torch.Tensor, n_voxe
     """Point -> voxel reduce (mmcv DynamicScatter of ref models/encoder.py:121-164); forward only."""
     seg_off, order = ops.csr_build(inverse_map.to(point_feats.device, torch.int64), n_voxels)
     return ops.segment_reduce(point_feats, seg_off, order, n_voxels, {"sum": 0, "mean": 1, "max": 2}[mode])
+
+
+# ---- the whole U-Net trunk as ONE autograd node (gcd_run_ops) ------------------------------------------------------
+class TrunkPlan:
+    """Static description of a MinkUNet trunk after the stem (ref models/minkunet.py:149-217): four encoder stages
+    (stride-2 conv-bn-relu + BasicBlocks) and four decoder stages (transposed conv-bn-relu, concatenation with the
+    encoder's output of the same resolution, BasicBlocks).  Built once per model from its modules; per step only
+    pointers and row counts change."""
+
+    def __init__(self, encoder, decoder):
+        # encoder / decoder: lists of (conv, bn, [BasicBlock, ...]) in forward order
+        self.encoder, self.decoder = encoder, decoder
+        self.units = []          # (conv module, MinkowskiBatchNorm module) of every conv-bn unit, in parameter order
+        for conv, bn, blocks in encoder + decoder:
+            self.units.append((conv, bn))
+            for blk in blocks:
+                self.units.append((blk.conv1, blk.norm1))
+                self.units.append((blk.conv2, blk.norm2))
+                if blk.downsample is not None:
+                    self.units.append((blk.downsample[0], blk.downsample[1]))
+        self.n_blocks = sum(1 + len(b) for _, _, b in encoder + decoder)
+        self.sum_c = sum(conv.out_channels for conv, _ in self.units)
+        self.sum_w = sum(conv.kernel.numel() for conv, _ in self.units)
+
+    def parameters(self):
+        out = []
+        for conv, bn in self.units:
+            out += [conv.kernel, bn.bn.weight, bn.bn.bias]
+        return out
+
+
+class _Bump:
+    """Bump allocator over one device buffer (all blocks of a pass share one allocation instead of ~5 tensors each)."""
+
+    def __init__(self, nbytes, device, zero=False):
+        self.buf = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+        self.base, self.off, self.cap = self.buf.data_ptr(), 0, max(nbytes, 256)
+
+    def take(self, nbytes):
+        off = self.off
+        self.off = (off + nbytes + 255) & ~255
+        if self.off > self.cap:
+            raise RuntimeError("internal error: trunk arena too small")
+        return self.base + off, off
+
+    def view(self, off, n, c, dtype):
+        return self.buf[off:off + n * c * dtype.itemsize].view(dtype).view(n, c)
+
+
+def _al(nbytes):
+    return (nbytes + 255) & ~255
+
+
+class TrunkFunction(torch.autograd.Function):
+    """Everything between the stem and the classifier head, forward and backward each ONE call into the library
+    (gcd_run_ops over the gcd_block_* sequences of every stage plus the column copies that stand for ME.cat).
+    Inputs: the stem's activation and the (kernel, gamma, beta) of every unit in ``plan.units`` order; outputs: the eight
+    stage outputs (block1 .. block8) the reference's forward variants hand out (ref models/minkunet.py:134-228)."""
+
+    @staticmethod
+    def forward(ctx, plan, mgr, x, *params):
+        from ._cabi import OP_BLOCK_FORWARD, OP_COPY_COLS, Op
+        xd = ops._rowmajor(x.detach())
+        dev, dt = xd.device, xd.dtype
+        esz = xd.element_size()
+        tc = dt == torch.bfloat16 and get_math_mode() == "bf16"
+        with_grad = any(ctx.needs_input_grad)
+        n_lv = [mgr.get_map(1 << l).n for l in range(5)]
+        # ---- arena sizes: every unit writes y and a ([n_out, c] each), every decoder stage one concatenated input
+        act_bytes, lvl = 0, 0
+        for conv, bn, blocks in plan.encoder:
+            lvl += 1
+            act_bytes += 2 * _al(n_lv[lvl] * conv.out_channels * esz)
+            for blk in blocks:
+                act_bytes += (6 if blk.downsample is not None else 4) * _al(n_lv[lvl] * blk.conv1.out_channels * esz)
+        for conv, bn, blocks in plan.decoder:
+            lvl -= 1
+            act_bytes += 2 * _al(n_lv[lvl] * conv.out_channels * esz) + _al(n_lv[lvl] * blocks[0].conv1.in_channels * esz)
+            for blk in blocks:
+                act_bytes += (6 if blk.downsample is not None else 4) * _al(n_lv[lvl] * blk.conv1.out_channels * esz)
+        act = _Bump(act_bytes, dev)
+        moments = torch.empty(2 * plan.sum_c, dtype=torch.float32, device=dev)
+        stats = ops.zeros_f64.take(2 * plan.sum_c, dev)
+        mptr, sptr = moments.data_ptr(), stats.data_ptr()
+        dtc = ops._dtype_code(xd)
+        blocks_c = (BlockArgs * plan.n_blocks)()
+        prog = (Op * (plan.n_blocks + 8))()
+        n_ops = bi = ci = pi = 0             # ops, blocks, channel offset into moments / stats, parameter index
+        sizes = []                            # weight elements per unit, in plan.units order
+
+        def unit(u, conv, bn, kmap, c_off):
+            w, g, b = params[pi_box[0]], params[pi_box[0] + 1], params[pi_box[0] + 2]
+            pi_box[0] += 3
+            sizes.append(_fill_unit(u, w, g, b, bn.fused_spec(), kmap, conv, tc and conv._pk_tc, with_grad))
+            c = conv.out_channels
+            u.stats, u.mean, u.invstd = sptr + 16 * c_off, mptr + 8 * c_off, mptr + 8 * c_off + 4 * c
+            return c
+
+        pi_box = [0]
+
+        def single(conv, bn, kmap, x_ptr, ld_x, n_out):
+            nonlocal bi, ci, n_ops
+            a = blocks_c[bi]
+            a.has_u2 = a.has_ud = 0
+            a.relu1, a.dtype, a.x, a.ld_x = 1, dtc, x_ptr, ld_x
+            c = unit(a.u1, conv, bn, kmap, ci)
+            ci += c
+            nb = n_out * c * esz
+            a.y1, _ = act.take(nb)
+            a.a1, off = act.take(nb)
+            prog[n_ops].op, prog[n_ops].block = OP_BLOCK_FORWARD, C.pointer(a)
+            n_ops += 1
+            bi += 1
+            return a.a1, off, c
+
+        def residual(blk, kmap3, kmap1, x_ptr, ld_x, n):
+            nonlocal bi, ci, n_ops
+            a = blocks_c[bi]
+            ds = blk.downsample
+            a.has_u2, a.has_ud, a.relu1, a.dtype, a.x, a.ld_x = 1, int(ds is not None), 1, dtc, x_ptr, ld_x
+            c = unit(a.u1, blk.conv1, blk.norm1, kmap3, ci)
+            unit(a.u2, blk.conv2, blk.norm2, kmap3, ci + c)
+            ci += 2 * c
+            nb = n * c * esz
+            a.y1, _ = act.take(nb)
+            a.a1, _ = act.take(nb)
+            a.y2, _ = act.take(nb)
+            a.out, off = act.take(nb)
+            if ds is not None:
+                unit(a.ud, ds[0], ds[1], kmap1, ci)
+                ci += c
+                a.yd, _ = act.take(nb)
+                a.rd, _ = act.take(nb)
+            prog[n_ops].op, prog[n_ops].block = OP_BLOCK_FORWARD, C.pointer(a)
+            n_ops += 1
+            bi += 1
+            return a.out, off, c
+
+        def copy_cols(dst, ld_dst, src, ld_src, n, c):
+            nonlocal n_ops
+            o = prog[n_ops]
+            o.op, o.dtype, o.dst, o.ld_dst, o.src, o.ld_src, o.n, o.c = OP_COPY_COLS, dtc, dst, ld_dst, src, ld_src, n, c
+            n_ops += 1
+
+        cur, ld, c_cur = xd.data_ptr(), ops._ld(xd), xd.shape[1]
+        skips = [(cur, ld, c_cur)]
+        outs = []                                                     # (offset, n, c) of block1 .. block8 outputs
+        for i, (conv, bn, blks) in enumerate(plan.encoder):
+            ts = 1 << i
+            n = n_lv[i + 1]
+            cur, off, c_cur = single(conv, bn, mgr.kernel_map(ts, 2, 2, False), cur, ld, n)
+            ld = c_cur
+            k3, k1 = mgr.kernel_map(2 * ts, 3, 1, False), mgr.kernel_map(2 * ts, 1, 1, False)
+            for blk in blks:
+                cur, off, c_cur = residual(blk, k3, k1, cur, ld, n)
+                ld = c_cur
+            outs.append((off, n, c_cur))
+            skips.append((cur, ld, c_cur))
+        for i, (conv, bn, blks) in enumerate(plan.decoder):
+            ts = 16 >> i
+            n = n_lv[3 - i]
+            up, _, c_up = single(conv, bn, mgr.kernel_map(ts, 2, 2, True), cur, ld, n)
+            s_ptr, s_ld, s_c = skips[3 - i]
+            c_cat = c_up + s_c
+            cat_ptr, _ = act.take(n * c_cat * esz)
+            copy_cols(cat_ptr, c_cat, up, c_up, n, c_up)                  # ME.cat(up, skip), ref models/minkunet.py:178-208
+            copy_cols(cat_ptr + c_up * esz, c_cat, s_ptr, s_ld, n, s_c)
+            cur, ld = cat_ptr, c_cat
+            k3, k1 = mgr.kernel_map(ts // 2, 3, 1, False), mgr.kernel_map(ts // 2, 1, 1, False)
+            for blk in blks:
+                cur, off, c_cur = residual(blk, k3, k1, cur, ld, n)
+                ld = c_cur
+            outs.append((off, n, c_cur))
+        launches = C.c_int32(0)
+        call("gcd_run_ops", prog, n_ops, ops._stream(), C.byref(launches))
+        ops._count(launches.value)
+        ctx.plan, ctx.blocks_c, ctx.sizes, ctx.n_lv, ctx.x_dtype, ctx.x_shape = plan, blocks_c, sizes, n_lv, x.dtype, tuple(xd.shape)
+        # everything the structs point into: input, arena, statistics, the kernel maps (tables, pair lists) of every level
+        ctx.keep = (xd, act, moments, [mgr.kernel_map(*k) for k in list(mgr._kmaps)])
+        ctx.set_materialize_grads(False)
+        return tuple(act.view(off, n, c, dt) for off, n, c in outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        from ._cabi import OP_ADD_COLS, OP_BLOCK_BACKWARD, Op
+        plan, blocks_c, sizes, n_lv = ctx.plan, ctx.blocks_c, ctx.sizes, ctx.n_lv
+        xd, act = ctx.keep[0], ctx.keep[1]
+        dev, dt = xd.device, xd.dtype
+        esz = xd.element_size()
+        dtc = ops._dtype_code(xd)
+        need_dx = ctx.needs_input_grad[2]
+        # ---- gradient arena: per block its three (one) gradient slabs and its input gradient(s)
+        gbytes = 0
+        for b in blocks_c:
+            nb = _al(b.u1.n_out * b.u1.c_out * esz)
+            gbytes += (3 if b.has_u2 else 1) * nb + (2 if b.has_ud else 1) * _al(b.u1.n_in * b.u1.c_in * esz)
+        garena = _Bump(gbytes, dev)
+        grads = ops.zeros_f32.take(plan.sum_w + 2 * plan.sum_c, dev)
+        sums = ops.zeros_f64.take(2 * plan.sum_c, dev)
+        gp, sp = grads.data_ptr(), sums.data_ptr()
+        prog = (Op * (plan.n_blocks + 16))()
+        n_ops = 0
+        # parameter-gradient slots, in plan.units order (weights first, then [dgamma | dbeta] of the unit)
+        unit_slots, woff, coff = [], 0, 0
+        for size, (conv, _) in zip(sizes, plan.units):
+            c = conv.out_channels
+            unit_slots.append((woff, size, plan.sum_w + 2 * coff, c, coff))
+            woff += size
+            coff += c
+        # units of block j, in plan order
+        ui = 0
+        block_units = []
+        for b in blocks_c:
+            k = 1 + int(b.has_u2) + int(b.has_ud)
+            block_units.append(list(range(ui, ui + k)))
+            ui += k
+
+        def add_cols(dst, ld_dst, src, ld_src, n, c):
+            nonlocal n_ops
+            o = prog[n_ops]
+            o.op, o.dtype, o.dst, o.ld_dst, o.src, o.ld_src, o.n, o.c = OP_ADD_COLS, dtc, dst, ld_dst, src, ld_src, n, c
+            n_ops += 1
+
+        def ext_grad(g, n, c):
+            """External gradient of a stage output as a dense buffer of the activation dtype (or None)."""
+            if g is None:
+                return None
+            g = ops._rowmajor(g)
+            if g.dtype != dt:
+                g = g.to(dt)
+            if g.shape[0] > 1 and g.stride(0) != c:
+                g = g.contiguous()
+            keep.append(g)
+            return g.data_ptr()
+
+        keep = []
+        # block index ranges per stage (forward order): encoder stage i = [single, blocks...], decoder likewise
+        stages, bi = [], 0
+        for conv, bn, blks in plan.encoder + plan.decoder:
+            stages.append((bi, bi + 1 + len(blks)))
+            bi += 1 + len(blks)
+        # gradient flowing into the output of block j (dense [n_out, c_out]); filled while walking backwards
+        g_in = [None] * plan.n_blocks
+        ld_in = [0] * plan.n_blocks
+        skip_extra = {}                        # last block of encoder stage s -> (ptr, ld, c_off) of the decoder's gradient slice
+        for s in range(7, -1, -1):
+            first, last = stages[s]
+            n_out, c_out = blocks_c[last - 1].u1.n_out, blocks_c[last - 1].u1.c_out
+            # gradient of the stage output: from the consumer inside the trunk (already in g_in) plus the caller's
+            eg = ext_grad(gouts[s], n_out, c_out)
+            if g_in[last - 1] is None:
+                if eg is None:
+                    raise RuntimeError("internal error: a trunk stage received no gradient")
+                g_in[last - 1], ld_in[last - 1] = eg, 0
+            elif eg is not None:
+                add_cols(g_in[last - 1], ld_in[last - 1] or c_out, eg, c_out, n_out, c_out)
+            if s in skip_extra:
+                ptr, ld_src = skip_extra[s]
+                add_cols(g_in[last - 1], ld_in[last - 1] or c_out, ptr, ld_src, n_out, c_out)
+            for j in range(last - 1, first - 1, -1):
+                b = blocks_c[j]
+                n_o, c_o, n_i, c_i = b.u1.n_out, b.u1.c_out, b.u1.n_in, b.u1.c_in
+                nb = n_o * c_o * esz
+                b.gout, b.ld_gout = g_in[j], ld_in[j]
+                stem_input = s == 0 and j == first
+                b.need_dx = int(need_dx or not stem_input)
+                if b.has_u2:
+                    b.dy2, _ = garena.take(nb)
+                    b.dres, _ = garena.take(nb)
+                    b.da1, _ = garena.take(nb)
+                    b.dy1, b.dyd = b.da1, b.dres       # in place: the first unit's BN backward on the second's dgrad, the shortcut's on the residual gradient
+                else:
+                    b.dy1, _ = garena.take(nb)
+                dx_off = None
+                if b.need_dx:
+                    b.dx, dx_off = garena.take(n_i * c_i * esz)
+                    if b.has_ud:
+                        b.dxd, _ = garena.take(n_i * c_i * esz)
+                for u, k in zip((b.u1, b.u2, b.ud), block_units[j]):
+                    wo, size, go, c, co = unit_slots[k]
+                    u.sums = sp + 16 * co
+                    u.dw, u.dgamma, u.dbeta = gp + 4 * wo, gp + 4 * go, gp + 4 * (go + c)
+                prog[n_ops].op, prog[n_ops].block = OP_BLOCK_BACKWARD, C.pointer(b)
+                n_ops += 1
+                if j > first:
+                    g_in[j - 1], ld_in[j - 1] = b.dx, 0
+                elif s >= 4:
+                    # first block of a decoder stage's residual chain is at first + 1; `first` is the transposed conv whose
+                    # input is the previous stage's output
+                    g_in[stages[s - 1][1] - 1], ld_in[stages[s - 1][1] - 1] = b.dx, 0
+                elif s > 0:
+                    g_in[stages[s - 1][1] - 1], ld_in[stages[s - 1][1] - 1] = b.dx, 0
+                else:
+                    dx_first = (dx_off, n_i, c_i) if b.need_dx else None
+                # the block right after a decoder stage's transposed conv reads [up | skip]: split its input gradient
+                if s >= 4 and j == first + 1:
+                    c_up = blocks_c[first].u1.c_out
+                    g_in[first], ld_in[first] = b.dx, c_i                      # left columns, strided
+                    skip_extra[7 - s - 1] = (b.dx + c_up * esz, c_i)           # right columns -> the encoder stage of that resolution
+        # the skip of tensor stride 1 is the trunk's input (the stem activation): its decoder slice joins dx of the first block
+        launches = C.c_int32(0)
+        if need_dx and -1 in skip_extra:
+            ptr, ld_src = skip_extra[-1]
+            add_cols(blocks_c[0].dx, 0 or blocks_c[0].u1.c_in, ptr, ld_src, blocks_c[0].u1.n_in, blocks_c[0].u1.c_in)
+        call("gcd_run_ops", prog, n_ops, ops._stream(), C.byref(launches))
+        ops._count(launches.value)
+        dx = None
+        if need_dx:
+            dx = garena.view(dx_first[0], dx_first[1], dx_first[2], dt)
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+        out = [None, None, dx]
+        for (wo, size, go, c, _), (conv, _) in zip(unit_slots, plan.units):
+            out += [grads[wo:wo + size].view(conv.kernel.shape), grads[go:go + c], grads[go + c:go + 2 * c]]
+        return tuple(out)

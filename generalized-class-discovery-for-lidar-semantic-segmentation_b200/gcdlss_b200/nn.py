@@ -12,7 +12,7 @@ import torch.nn as nn
 from . import ops
 from .config import get_math_mode
 from .functional import (BasicBlockFunction, BatchNormActFunction, ConvBnActFunction, FusedBlockFunction, Im2colFunction, ReLUFunction,
-                         SparseConvFunction, _BnSpec, fused_block_ok, packed_weights)
+                         SparseConvFunction, TrunkFunction, TrunkPlan, _BnSpec, fused_block_ok, packed_weights)
 from .sparse_tensor import CoordinateMapKey, SparseTensor
 
 
@@ -235,6 +235,42 @@ def conv_bn_act(conv, bn, x: SparseTensor, relu: bool = True) -> SparseTensor:
     else:
         out = ConvBnActFunction.apply(feats, conv.kernel, bn.bn.weight, bn.bn.bias, kmap, conv, bn.fused_spec(), relu, out_dtype)
     return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
+
+
+def _block_fusable(blk) -> bool:
+    ds = blk.downsample
+    return (isinstance(blk, BasicBlock) and blk.conv1.stride == 1 and blk.conv1.bias is None and blk.conv2.bias is None and
+            (ds is None or (isinstance(ds, nn.Sequential) and len(ds) == 2 and isinstance(ds[0], MinkowskiConvolution) and
+                            isinstance(ds[1], MinkowskiBatchNorm) and ds[0].kernel_volume == 1 and ds[0].stride == 1 and ds[0].bias is None)))
+
+
+def trunk_plan(encoder, decoder):
+    """TrunkPlan of a U-Net made of (conv, bn, nn.Sequential of BasicBlocks) stages, or None when some layer is outside what
+    gcd_run_ops sequences (Bottleneck blocks, biases, channel counts the tensor-core path cannot take)."""
+    stages = [(conv, bn, list(blocks)) for conv, bn, blocks in encoder + decoder]
+    for conv, bn, blocks in stages:
+        if conv.bias is not None or not isinstance(bn, MinkowskiBatchNorm) or conv.kernel_volume != 8 or not blocks:
+            return None
+        if not all(_block_fusable(b) for b in blocks):
+            return None
+        convs = [conv] + [c for b in blocks for c in ((b.conv1, b.conv2) + ((b.downsample[0],) if b.downsample is not None else ()))]
+        if not all(c._pk_tc for c in convs):
+            return None
+    return TrunkPlan(stages[:len(encoder)], stages[len(encoder):])
+
+
+def run_trunk(plan, x: SparseTensor):
+    """The eight stage outputs (SparseTensors) of a planned trunk from the stem's output, as one autograd node; None when the
+    fast path does not apply right now (evaluation mode, instrumentation, mixed dtypes)."""
+    feats = x._F
+    training = all(bn.bn.training for _, bn in plan.units)
+    bf16 = get_math_mode() == "bf16"
+    if not fused_block_ok(feats, torch.bfloat16 if bf16 else torch.float32, training) or x.tensor_stride_int != 1:
+        return None
+    mgr = x.coordinate_manager
+    outs = TrunkFunction.apply(plan, mgr, feats, *plan.parameters())
+    strides = (2, 4, 8, 16, 8, 4, 2, 1)
+    return [SparseTensor(o, coordinate_map_key=CoordinateMapKey(ts), coordinate_manager=mgr) for o, ts in zip(outs, strides)]
 
 
 def cat(*tensors) -> SparseTensor:

@@ -12,8 +12,6 @@ Lightning (not installable here).  They exist so the path can be exercised and t
 """
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn.functional as F
 
@@ -130,6 +128,44 @@ def mix_transform(sup_data, unsup_data, mix_unsup_pseudo_labels, num_areas, pitc
     return torch.cat(rows).float(), torch.cat(feats).float(), torch.cat(labs).int()
 
 
+def make_stage2_half(kind: str, idx0: int, n_scans: int, n_points, dev, with_labels: bool, n_classes: int = 17, host_scans=None):
+    """One half (labelled or unlabelled) of a Stage-2 batch from synthetic scans ``idx0 .. idx0 + n_scans - 1``, laid out
+    like the reference's collate output (ref utils/collation.py:430-467) and quantised on the GPU: voxel-level
+    'coords' / 'feats' (/ 'labels'), point-level 'points' dict, 'inverse_maps' for the unlabelled half.
+    ``host_scans``: optional list of (points [P, 4] pinned host tensor (x, y, z, remission), labels [P]) to start from host
+    memory (bench.py's end-to-end loop); otherwise the scans are generated here."""
+    import numpy as np
+
+    from . import synth
+    q = synth.voxel_size(kind)
+    coords, feats, labels, pcoords, pfeats, plabels, invs = [], [], [], [], [], [], []
+    for b in range(n_scans):
+        if host_scans is not None:
+            pts, lab = host_scans[b]
+            pts, lab = pts.to(dev, non_blocking=True), lab.to(dev, non_blocking=True)
+            p, ff = pts[:, :3].contiguous(), pts[:, 3:4].contiguous()
+        else:
+            xyz, f = synth.make_scan(kind, idx0 + b, n_points=n_points)
+            p, ff = torch.from_numpy(xyz).to(dev), torch.from_numpy(f).to(dev)
+            lab = torch.from_numpy(np.random.default_rng(idx0 + b).integers(0, n_classes, xyz.shape[0])).to(dev)
+        c, um, inv = sparse_quantize_gpu(p, q)
+        coords.append(torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int32, device=dev), c], 1))
+        feats.append(ff[um])
+        labels.append(lab[um])
+        pcoords.append(torch.cat([torch.full((p.shape[0], 1), float(b), device=dev), p], 1))
+        pfeats.append(ff)
+        plabels.append(lab)
+        invs.append(inv)
+    d = {"coords": torch.cat(coords), "feats": torch.cat(feats), "n_scans": n_scans,
+         "points": {"coords": torch.cat(pcoords), "feats": torch.cat(pfeats)}}
+    if with_labels:
+        d["labels"] = torch.cat(labels)
+        d["points"]["mapped_labels"] = torch.cat(plabels)
+    else:
+        d["inverse_maps"] = invs
+    return d
+
+
 class Stage2Harness:
     def __init__(self, student, teacher, optimizer, voxel_size: float, mse_coeff: float = 200.0, ema_momentum: float = 0.01,
                  num_areas=(3, 4, 5, 6), reducer=None, fused_loss: bool = False):
@@ -142,10 +178,11 @@ class Stage2Harness:
             p.requires_grad_(False)                                        # ref :155, :251-254
 
     def step(self, sup, unsup):
-        """sup / unsup: dicts with voxel-level 'coords' [M,4] int32, 'feats' [M,C], point-level 'points' (list of [P,3]),
-        'point_feats' (list of [P,C]); sup also 'labels' [M] (voxels) and 'point_labels' (list of [P]); unsup also
-        'inverse_maps' (list of [P] int64, voxel of each point *within its scan*)."""
-        n_sup_scans = len(sup["points"])
+        """sup / unsup: what the Stage-2 collate hands the reference's training_step (ref :2774-2793), on the device:
+        voxel level 'coords' [M, 4] int32, 'feats' [M, C]; point level 'points' = {'coords' [P, 4] float (batch, x, y, z),
+        'feats' [P, C]}; sup also 'labels' [M] (voxels) and points['mapped_labels'] [P]; unsup also 'inverse_maps' (list of
+        [P_i] int64, voxel of each point *within its scan*)."""
+        n_sup_scans = int(sup["coords"][:, 0].max().item()) + 1 if "n_scans" not in sup else sup["n_scans"]
         unsup_coords = unsup["coords"].clone()
         unsup_coords[:, 0] += n_sup_scans                                  # ref :2797
         coords_cat = torch.cat((sup["coords"], unsup_coords), 0)
@@ -170,26 +207,15 @@ class Stage2Harness:
         pts_prob = devoxelize(max_prob_t[:, None], inv_cat)[:, 0]
         pts_label = devoxelize(target_t[:, None].float(), inv_cat)[:, 0].long()
         pts_label[pts_prob < 0.9] = -1
-        # LaserMix: scan i of the labelled half with scan i of the unlabelled half
-        areas = self.num_areas[self._step % len(self.num_areas)]
-        mixed_pts, mixed_feats, mixed_labels = [], [], []
-        off = 0
-        for i in range(min(n_sup_scans, len(unsup["points"]))):
-            pu = unsup["points"][i]
-            lu = pts_label[off:off + pu.shape[0]]
-            off += pu.shape[0]
-            for b, (mp, mf, ml) in enumerate(laser_mix(sup["points"][i], pu, sup["point_feats"][i], unsup["point_feats"][i],
-                                                       sup["point_labels"][i], lu, areas)):
-                bcol = torch.full((mp.shape[0], 1), float(2 * i + b), device=mp.device)
-                mixed_pts.append(torch.cat([bcol, mp], 1))
-                mixed_feats.append(mf)
-                mixed_labels.append(ml)
-        lm_points = torch.cat(mixed_pts)
+        # LaserMix (ref :2854 -> mix_transform): scan 0 with scan 0, the rest with the rest; the band counts are this
+        # step's draws (the reference draws them with np.random.choice inside laser_mix_transform)
+        areas = [self.num_areas[(2 * self._step + j) % len(self.num_areas)] for j in range(2)]
+        lm_points, lm_feats, lm_labels = mix_transform(sup["points"], unsup["points"], pts_label, areas)
         # inline quantisation of the mixed batch: the batch column is divided by the voxel size too (ref :2856-2861)
         lm_coords, lm_umap, _ = sparse_quantize_gpu(lm_points, self.voxel_size)
-        mix_st = SparseTensor(features=torch.cat(mixed_feats)[lm_umap].float(), coordinates=lm_coords)
+        mix_st = SparseTensor(features=lm_feats[lm_umap].float(), coordinates=lm_coords)      # the first point of a voxel represents it (ref :2864)
         out_mix = self.student(mix_st)
-        mix_labels = torch.cat(mixed_labels)[lm_umap]
+        mix_labels = lm_labels[lm_umap]
         if bool((mix_labels >= 0).any()):
             loss = loss + 0.1 * point_cross_entropy(out_mix["logits"], mix_labels.long(), ignore_index=-1)
         else:

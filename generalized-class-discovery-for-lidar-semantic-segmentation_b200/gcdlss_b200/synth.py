@@ -95,4 +95,4 @@ def make_dense_scan(index: int = 0, sweeps: int = 10):
 
 
 def voxel_size(kind: str) -> float:
-    return PRESETS[kind][4]
+    return PRESETS["kitti" if kind == "dense" else kind][4]

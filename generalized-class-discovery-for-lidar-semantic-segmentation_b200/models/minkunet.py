@@ -12,7 +12,7 @@ import torch.nn.functional as F
 import MinkowskiEngine as ME
 from MinkowskiEngine.modules.resnet_block import BasicBlock, Bottleneck
 
-from gcdlss_b200.nn import conv_bn_act
+from gcdlss_b200.nn import conv_bn_act, run_trunk, trunk_plan
 
 from models.resnet import ResNetBase
 
@@ -71,6 +71,16 @@ class _UNetTrunk(ResNetBase):
     def _trunk(self, x):
         """Returns the outputs of block1..block8 (index 0 = block1)."""
         cur = conv_bn_act(self.conv0p1s1, self.bn0, x)
+        # training fast path: everything after the stem as ONE autograd node / two library calls (gcd_run_ops)
+        plan = self.__dict__.get("_trunk_plan", False)
+        if plan is False:
+            plan = trunk_plan([(getattr(self, c), getattr(self, b), getattr(self, k)) for c, b, k in _ENCODER],
+                              [(getattr(self, c), getattr(self, b), getattr(self, k)) for c, b, k in _DECODER])
+            self.__dict__["_trunk_plan"] = plan
+        if plan is not None:
+            stages = run_trunk(plan, cur)
+            if stages is not None:
+                return stages
         skips, stages = [cur], []
         for conv, bn, block in _ENCODER:
             cur = conv_bn_act(getattr(self, conv), getattr(self, bn), cur)

@@ -83,7 +83,8 @@ typedef enum {
   GCD_OPT_TC_STAGES = 2,     /* > 0: cap on the shared-memory ring depth of the tcgen05 convolution (tuning aid) */
   GCD_OPT_TC_GROUP = 3,      /* 1 | 2 | 4 | 8: gather warps per ring slot; 0 = chosen per launch (tuning aid) */
   GCD_OPT_WG_CHUNK_MIN = 4,  /* > 0: minimum pairs per wgrad work item (tuning aid) */
-  GCD_OPT_COUNT_ = 5
+  GCD_OPT_TC_WARPS = 5,      /* 8 | 16: gather warps per CTA of the tcgen05 forward / dgrad kernel */
+  GCD_OPT_COUNT_ = 6
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);
@@ -357,10 +358,31 @@ typedef struct {
   void* dy2; void* dres; void* da1; void* dy1; void* dyd; void* dx; void* dxd;
   int32_t need_dx;
   int32_t launches;          /* out: kernels launched by the call */
+  int64_t ld_gout;           /* leading dimension of gout; 0 = dense (the width of the block's output) */
 } gcd_block_args;
 
 int32_t gcd_block_forward(gcd_block_args* args, void* stream);
 int32_t gcd_block_backward(gcd_block_args* args, void* stream);
+
+/* A whole network pass as ONE call: the host fills an array of operations (blocks and the column copies / adds that
+ * stand for ME.cat and its backward, ref models/minkunet.py:178-208) and the library issues them in order on `stream`.
+ * With one call per block the MinkUNet34 step costs the host ~70 calls and as many autograd nodes; with this it is two.
+ *   GCD_OP_BLOCK_FORWARD / _BACKWARD : gcd_block_forward / gcd_block_backward on `block`
+ *   GCD_OP_COPY_COLS : dst[i, 0:c] = src[i, 0:c]  for i < n   (row pitches ld_dst / ld_src, elements of `dtype`)
+ *   GCD_OP_ADD_COLS  : dst[i, 0:c] += src[i, 0:c]
+ * c, both pitches and both pointers must be multiples of 16 bytes.  *launches (host, optional) receives the kernel count. */
+typedef enum { GCD_OP_BLOCK_FORWARD = 0, GCD_OP_BLOCK_BACKWARD = 1, GCD_OP_COPY_COLS = 2, GCD_OP_ADD_COLS = 3 } gcd_op_kind;
+typedef struct {
+  int32_t op;                /* gcd_op_kind */
+  int32_t dtype;             /* gcd_dtype (copy / add) */
+  gcd_block_args* block;     /* block operations */
+  void* dst; int64_t ld_dst;
+  const void* src; int64_t ld_src;
+  int64_t n;
+  int32_t c;
+  int32_t reserved;
+} gcd_op;
+int32_t gcd_run_ops(gcd_op* ops, int32_t n_ops, void* stream, int32_t* launches);
 
 #ifdef __cplusplus
 }

@@ -67,20 +67,23 @@ def test_block_struct_layout_against_gcc(tmp_path):
     """sizeof / offsetof of the fused-block structs as gcc lays them out == the ctypes mirror."""
     fields_u = [f[0] for f in _cabi.ConvBnUnit._fields_]
     fields_b = [f[0] for f in _cabi.BlockArgs._fields_]
+    fields_o = [f[0] for f in _cabi.Op._fields_]
     prog = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{HEADER}"', "int main(void){",
-            'printf("%zu %zu\\n", sizeof(gcd_convbn), sizeof(gcd_block_args));']
+            'printf("%zu %zu %zu\\n", sizeof(gcd_convbn), sizeof(gcd_block_args), sizeof(gcd_op));']
     prog += [f'printf("%zu\\n", offsetof(gcd_convbn, {f}));' for f in fields_u]
     prog += [f'printf("%zu\\n", offsetof(gcd_block_args, {f}));' for f in fields_b]
+    prog += [f'printf("%zu\\n", offsetof(gcd_op, {f}));' for f in fields_o]
     prog += ["return 0;}"]
     src = tmp_path / "layout.c"
     src.write_text("\n".join(prog))
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-    sizes, offs = [int(v) for v in out[:2]], [int(v) for v in out[2:]]
-    assert sizes == [ctypes.sizeof(_cabi.ConvBnUnit), ctypes.sizeof(_cabi.BlockArgs)]
+    sizes, offs = [int(v) for v in out[:3]], [int(v) for v in out[3:]]
+    assert sizes == [ctypes.sizeof(_cabi.ConvBnUnit), ctypes.sizeof(_cabi.BlockArgs), ctypes.sizeof(_cabi.Op)]
     assert offs[:len(fields_u)] == [getattr(_cabi.ConvBnUnit, f).offset for f in fields_u]
-    assert offs[len(fields_u):] == [getattr(_cabi.BlockArgs, f).offset for f in fields_b]
+    assert offs[len(fields_u):len(fields_u) + len(fields_b)] == [getattr(_cabi.BlockArgs, f).offset for f in fields_b]
+    assert offs[len(fields_u) + len(fields_b):] == [getattr(_cabi.Op, f).offset for f in fields_o]
 
 
 def test_product_code_never_imports_the_oracle():

@@ -141,3 +141,52 @@ def test_fused_path_is_taken(cuda):
         assert seen and ops.launch_counter["calls"] - n0 == 6
     finally:
         _cabi._fn_cache["gcd_block_forward"] = orig
+
+
+@pytest.mark.parametrize("mode,arch", [("bf16", "MinkUNet34C"), ("fp32", "MinkUNet34C"), ("bf16", "MinkUNet14A")])
+def test_trunk_fast_path_equals_the_per_block_path(cuda, mode, arch):
+    """functional.TrunkFunction (the whole trunk as one autograd node, gcd_run_ops) launches the same kernels in the same
+    order as the per-block Functions: identical stage outputs bit for bit, gradients equal up to the summation order of the
+    atomics in wgrad / the BN reductions."""
+    import gcdlss_b200
+    import MinkowskiEngine as ME
+    from gcdlss_b200 import ops
+    from models import minkunet as mu
+    from oracle import quantize as oq
+    from gcdlss_b200 import synth
+    prev = gcdlss_b200.get_math_mode()
+    gcdlss_b200.set_math_mode(mode)
+    try:
+        coords, feats = [], []
+        for i in range(2):
+            xyz, f = synth.make_scan("kitti", i, n_points=20000)
+            c, um, _ = oq.sparse_quantize_me(xyz, 0.05)
+            coords.append(c)
+            feats.append(f[um])
+        bc = torch.from_numpy(oq.batched_coordinates(coords)).cuda()
+        f = torch.from_numpy(np.concatenate(feats)).cuda()
+        labels = torch.randint(0, 17, (bc.shape[0],), device="cuda")
+        torch.manual_seed(0)
+        model = getattr(mu, arch)(1, 17).cuda().train()
+        res = []
+        for fast in (True, False):
+            model.zero_grad(set_to_none=True)
+            model.__dict__.pop("_trunk_plan", None)
+            if not fast:
+                model.__dict__["_trunk_plan"] = None
+            n0 = ops.launch_counter["calls"]
+            stages = model._trunk(ME.SparseTensor(features=f, coordinates=bc))
+            logits = model.final(stages[7]).F
+            loss = torch.nn.functional.cross_entropy(logits.float(), labels) + 0.01 * stages[3].F.float().square().mean()     # a tap on the bottleneck too
+            loss.backward()
+            res.append(([s.F.detach().clone() for s in stages], torch.cat([p.grad.flatten().float() for p in model.parameters()]),
+                        ops.launch_counter["calls"] - n0))
+        model.__dict__.pop("_trunk_plan", None)
+        (s_fast, g_fast, n_fast), (s_slow, g_slow, n_slow) = res
+        for a, b in zip(s_fast, s_slow):
+            assert a.dtype == b.dtype and torch.equal(a, b)
+        cos = float(torch.nn.functional.cosine_similarity(g_fast, g_slow, dim=0))
+        print(mode, arch, "gradient cosine fast vs per-block", cos, "max abs diff", float((g_fast - g_slow).abs().max()), "launches", n_fast, n_slow)
+        assert cos > 0.9999 and torch.isfinite(g_fast).all()
+    finally:
+        gcdlss_b200.set_math_mode(prev)

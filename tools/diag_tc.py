@@ -73,8 +73,13 @@ for (cin, cout, ts, ks) in layers:
     dw = torch.zeros_like(w)
     us_w = timeit(lambda: ops.conv_wgrad(x, g, km.pairs, kv, dw, math_mode=1))
     print(f"{cin}->{cout} ts{ts} K{ks}: n={n} pairs={pairs} density={pairs / (kv * n):.2f} | wgrad {us_w:.1f} us {flops / us_w / 1e6:.1f} TFLOP/s")
-    for name, fn in variants.items():
-        us = timeit(fn)
-        print(f"    fwd {name:13s} {us:7.1f} us  {flops / us / 1e6:6.1f} TFLOP/s alg")
-        if profile:
-            print("        " + counters(fn))
+    for warps in (8, 16):
+        _cabi.lib().gcd_set_option(_cabi.OPT_TC_WARPS, warps)
+        for name, fn in variants.items():
+            if warps == 16 and name == "scan":
+                continue
+            us = timeit(fn)
+            print(f"    fwd {name:13s} warps={warps:2d} {us:7.1f} us  {flops / us / 1e6:6.1f} TFLOP/s alg")
+            if profile:
+                print("        " + counters(fn))
+    _cabi.lib().gcd_set_option(_cabi.OPT_TC_WARPS, 8)

@@ -39,7 +39,6 @@ constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueThreads = 128;
 constexpr int kEpilogueWarp0 = kProducerWarps;        // 8: (8 + i) % 4 == i, the TMEM lane quarter rule
 constexpr int kMmaWarp = kProducerWarps + 4;          // 12
-constexpr int kTableWarp = kProducerWarps + 5;        // 13 (forward kernel: stages the neighbour-table slices)
 constexpr int kTcThreads = kProducerThreads + kEpilogueThreads + 64;
 constexpr int kMaxKV = 27;
 constexpr int kMaxStages = 8;
@@ -413,6 +412,7 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
   } else if (warp < kMma) {
     // ===================================================================== epilogue
     const int ew = warp - kEpi0;      // == warp % 4: the TMEM lane quarter this warp may read
+    const bool wide_store = p.out_is_bf16 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && (p.ld_out & 15) == 0;   // every 16-column chunk 32-byte aligned
     uint32_t tile_seq = 0;
 #ifdef GCD_TC_PROFILE
     long long prof_ewait = 0; const long long prof_t0 = clock64();
@@ -421,6 +421,9 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
       const int64_t tm = work / p.n_tiles_n;
       const int tn = (int)(work - tm * p.n_tiles_n);
       const uint32_t buf = tile_seq & 1;
+      const int64_t row = tm * kTileM + ew * 32 + lane;
+      int64_t orow = row;                        // where this accumulator lane's row goes
+      if constexpr (kPerm) { if (row < p.n_out) orow = __ldg(&p.out_rows[row]); }     // issued before the wait: its latency hides behind the tile's MMAs
 #ifdef GCD_TC_PROFILE
       const long long cew0 = clock64();
 #endif
@@ -429,9 +432,6 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
       prof_ewait += clock64() - cew0;
 #endif
       tc_fence_after();
-      const int64_t row = tm * kTileM + ew * 32 + lane;
-      int64_t orow = row;                        // where this accumulator lane's row goes
-      if constexpr (kPerm) { if (row < p.n_out) orow = p.out_rows[row]; }
       const int col0 = tn * p.n_tile_cols;
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)(ew * 32) << 16);
       for (int c = 0; c < p.n_tile_cols; c += 16) {
@@ -450,8 +450,11 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
               __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
               w[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            if (wide_store) st_global_v8(o, w);      // one 32-byte store per lane: half the LSU work of two 16-byte ones (the LSU is the gather's resource)
+            else {
+              *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
           } else {
             float* o = reinterpret_cast<float*>(p.out) + orow * p.ld_out + col0 + c;
 #pragma unroll

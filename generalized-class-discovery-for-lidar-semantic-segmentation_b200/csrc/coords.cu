@@ -399,6 +399,29 @@ extern "C" int32_t gcd_kmap_subm(const int32_t* coords, int64_t n, const uint64_
   return GCD_OK;
 }
 
+namespace gcd { namespace {
+struct Affine { double m[12]; };
+__global__ void __launch_bounds__(256) affine_f64_kernel(const float* __restrict__ pts, int64_t ld, int64_t n, const Affine a, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = (double)pts[i * ld], y = (double)pts[i * ld + 1], z = (double)pts[i * ld + 2];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    out[i * 3 + j] = fma(z, a.m[4 * j + 2], fma(y, a.m[4 * j + 1], x * a.m[4 * j])) + a.m[4 * j + 3];
+}
+} }
+
+extern "C" int32_t gcd_affine_f64(const float* pts, int64_t ld, int64_t n, const double* m_host, double* out, void* stream) {
+  GCD_REQUIRE(n >= 0 && ld >= 3 && m_host != nullptr, "gcd_affine_f64: bad arguments");
+  if (n == 0) return GCD_OK;
+  GCD_REQUIRE(pts && out, "gcd_affine_f64: null pointer");
+  Affine a;
+  for (int i = 0; i < 12; ++i) a.m[i] = m_host[i];
+  affine_f64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(pts, ld, n, a, out);
+  GCD_LAUNCH_CHECK("gcd_affine_f64");
+  return GCD_OK;
+}
+
 extern "C" int32_t gcd_kmap_down2(const int32_t* parent, const int32_t* code, int64_t n_fine, int64_t n_coarse, int32_t* nbr,
                                   void* stream) {
   cudaStream_t st = as_stream(stream);

@@ -126,6 +126,13 @@ __device__ __forceinline__ void bulk_g2s_pred(uint32_t dst_smem, const void* src
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "r"(pred) : "memory");
 }
 
+// 32-byte global store (sm_100: STG.E.256); the address must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // 16-byte vector reduction (sm_90+): four fp32 adds in one L2 operation
 __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -129,6 +129,7 @@ PROTOTYPES = {
     "gcd_get_option": (_i32, [_i32]),
     "gcd_quantize_f32": (_i32, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp]),
     "gcd_quantize_f64": (_i32, [_vp, _i64, _i64, _i32, _f64, _i32, _vp, _vp]),
+    "gcd_affine_f64": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "gcd_colmin_i32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "gcd_sub_cols_i32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "gcd_hash_capacity": (_i64, [_i64]),

@@ -467,6 +467,16 @@ def voxelize_reduce(point_feats: torch.Tensor, inverse_map: torch.Tensor, n_voxe
 
 
 # ---- the whole U-Net trunk as ONE autograd node (gcd_run_ops) ------------------------------------------------------
+def shortcut_pair(ds):
+    """(1x1 convolution, batch norm) of a residual block's ``downsample`` module: ``nn.Sequential(conv, bn)`` as ResNetBase
+    builds it (ref models/resnet.py:100-113), or a conv module that carries that Sequential as ``.net`` (mmdet3d's
+    MinkowskiConvModule without activation, ref models/backbone.py:160-166).  None when it is anything else."""
+    seq = getattr(ds, "net", ds)
+    if isinstance(seq, torch.nn.Sequential) and len(seq) == 2:
+        return seq[0], seq[1]
+    return None
+
+
 class TrunkPlan:
     """Static description of a MinkUNet trunk after the stem (ref models/minkunet.py:149-217): four encoder stages
     (stride-2 conv-bn-relu + BasicBlocks) and four decoder stages (transposed conv-bn-relu, concatenation with the
@@ -483,7 +493,7 @@ class TrunkPlan:
                 self.units.append((blk.conv1, blk.norm1))
                 self.units.append((blk.conv2, blk.norm2))
                 if blk.downsample is not None:
-                    self.units.append((blk.downsample[0], blk.downsample[1]))
+                    self.units.append(shortcut_pair(blk.downsample))
         self.n_blocks = sum(1 + len(b) for _, _, b in encoder + decoder)
         self.sum_c = sum(conv.out_channels for conv, _ in self.units)
         self.sum_w = sum(conv.kernel.numel() for conv, _ in self.units)
@@ -593,7 +603,7 @@ class TrunkFunction(torch.autograd.Function):
             a.y2, _ = act.take(nb)
             a.out, off = act.take(nb)
             if ds is not None:
-                unit(a.ud, ds[0], ds[1], kmap1, ci)
+                unit(a.ud, *shortcut_pair(ds), kmap1, ci)
                 ci += c
                 a.yd, _ = act.take(nb)
                 a.rd, _ = act.take(nb)

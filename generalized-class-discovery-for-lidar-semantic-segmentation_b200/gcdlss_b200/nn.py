@@ -12,7 +12,7 @@ import torch.nn as nn
 from . import ops
 from .config import get_math_mode
 from .functional import (BasicBlockFunction, BatchNormActFunction, ConvBnActFunction, FusedBlockFunction, Im2colFunction, ReLUFunction,
-                         SparseConvFunction, TrunkFunction, TrunkPlan, _BnSpec, fused_block_ok, packed_weights)
+                         SparseConvFunction, TrunkFunction, TrunkPlan, _BnSpec, fused_block_ok, packed_weights, shortcut_pair)
 from .sparse_tensor import CoordinateMapKey, SparseTensor
 
 
@@ -237,11 +237,15 @@ def conv_bn_act(conv, bn, x: SparseTensor, relu: bool = True) -> SparseTensor:
     return SparseTensor(out, coordinate_map_key=CoordinateMapKey(ts_out), coordinate_manager=mgr)
 
 
+def _shortcut_ok(ds) -> bool:
+    pair = shortcut_pair(ds)
+    return (pair is not None and isinstance(pair[0], MinkowskiConvolution) and isinstance(pair[1], MinkowskiBatchNorm) and
+            pair[0].kernel_volume == 1 and pair[0].stride == 1 and pair[0].bias is None)
+
+
 def _block_fusable(blk) -> bool:
-    ds = blk.downsample
     return (isinstance(blk, BasicBlock) and blk.conv1.stride == 1 and blk.conv1.bias is None and blk.conv2.bias is None and
-            (ds is None or (isinstance(ds, nn.Sequential) and len(ds) == 2 and isinstance(ds[0], MinkowskiConvolution) and
-                            isinstance(ds[1], MinkowskiBatchNorm) and ds[0].kernel_volume == 1 and ds[0].stride == 1 and ds[0].bias is None)))
+            (blk.downsample is None or _shortcut_ok(blk.downsample)))
 
 
 def trunk_plan(encoder, decoder):
@@ -253,7 +257,7 @@ def trunk_plan(encoder, decoder):
             return None
         if not all(_block_fusable(b) for b in blocks):
             return None
-        convs = [conv] + [c for b in blocks for c in ((b.conv1, b.conv2) + ((b.downsample[0],) if b.downsample is not None else ()))]
+        convs = [conv] + [c for b in blocks for c in ((b.conv1, b.conv2) + ((shortcut_pair(b.downsample)[0],) if b.downsample is not None else ()))]
         if not all(c._pk_tc for c in convs):
             return None
     return TrunkPlan(stages[:len(encoder)], stages[len(encoder):])
@@ -318,10 +322,7 @@ class BasicBlock(nn.Module):
 
     def forward(self, x: SparseTensor) -> SparseTensor:
         ds = self.downsample
-        fusable = (self.conv1.stride == 1 and self.conv1.bias is None and self.conv2.bias is None and
-                   (ds is None or (isinstance(ds, nn.Sequential) and len(ds) == 2 and isinstance(ds[0], MinkowskiConvolution) and
-                                   isinstance(ds[1], MinkowskiBatchNorm) and ds[0].kernel_volume == 1 and ds[0].stride == 1 and
-                                   ds[0].bias is None)))
+        fusable = self.conv1.stride == 1 and self.conv1.bias is None and self.conv2.bias is None and (ds is None or _shortcut_ok(ds))
         if not fusable:
             shortcut = x if ds is None else ds(x)
             y = self.norm1(self.conv1(x), relu=True)
@@ -335,10 +336,11 @@ class BasicBlock(nn.Module):
         if out_dtype == torch.bfloat16 and feats.dtype != torch.bfloat16:
             feats = feats.to(torch.bfloat16)
         if ds is None:
-            wd = gd = bd = hd = bnd = None
+            wd = gd = bd = hd = bnd = ds_bn = None
         else:
-            wd, gd, bd, hd, bnd = ds[0].kernel, ds[1].bn.weight, ds[1].bn.bias, ds[0], ds[1].fused_spec()
-        if fused_block_ok(feats, out_dtype, self.norm1.bn.training and self.norm2.bn.training and (ds is None or ds[1].bn.training)):
+            ds_conv, ds_bn = shortcut_pair(ds)
+            wd, gd, bd, hd, bnd = ds_conv.kernel, ds_bn.bn.weight, ds_bn.bn.bias, ds_conv, ds_bn.fused_spec()
+        if fused_block_ok(feats, out_dtype, self.norm1.bn.training and self.norm2.bn.training and (ds is None or ds_bn.bn.training)):
             out = FusedBlockFunction.apply(feats, self.conv1.kernel, self.norm1.bn.weight, self.norm1.bn.bias, self.conv2.kernel,
                                            self.norm2.bn.weight, self.norm2.bn.bias, wd, gd, bd, kmap3, kmap1, (self.conv1, self.conv2, hd),
                                            (self.norm1.fused_spec(), self.norm2.fused_spec(), bnd), True)

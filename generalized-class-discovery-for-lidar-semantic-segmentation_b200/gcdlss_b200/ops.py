@@ -137,6 +137,21 @@ def quantize(points: torch.Tensor, q: float, dims: int, round_mode: int) -> torc
     return out
 
 
+def affine_f64(points: torch.Tensor, matrix) -> torch.Tensor:
+    """float64 [n, 3] = [points | 1] @ matrix.T[:, :3] for float32 CUDA points [n, >= 3] and a 4x4 (or 3x4) float64 host matrix
+    (the dataset's rigid / voxelisation transform, ref utils/dataset_remission.py:821-833)."""
+    import numpy as np
+    _require_cuda(points)
+    if points.dtype != torch.float32:
+        raise TypeError("points must be float32 (the datasets read float32 scans)")
+    points = _rowmajor(points)
+    m = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64)[:3, :4])
+    out = torch.empty((points.shape[0], 3), dtype=torch.float64, device=points.device)
+    call("gcd_affine_f64", _ptr(points), _ld(points), points.shape[0], m.ctypes.data_as(C.c_void_p), _ptr(out), _stream())
+    _count()
+    return out
+
+
 def shift_to_min(coords: torch.Tensor) -> torch.Tensor:
     """coords -= coords.min(0), in place (ref models/voxelizer.py:276)."""
     n, dims = coords.shape

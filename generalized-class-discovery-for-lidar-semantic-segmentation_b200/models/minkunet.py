@@ -123,9 +123,32 @@ class MinkUNetBaseRC(_UNetTrunk):
         assert isinstance(layers, list), 'layers should be a list.'
         return self._trunk(x)[7]
 
+    def _heads(self, feat, names):
+        """The 1x1 classifier heads ``names`` (final / final2 / final3, ref models/minkunet.py:312-362 and the heads the
+        Lightning module bolts on, ref modules/exp_merge_mean_teacher.py:128-153) applied to the same 96-channel features
+        as ONE 96 -> sum(C_i) product instead of one per head: one forward, one dgrad and one wgrad launch for all of them
+        (the features are read once each way).  Returns the per-head logits (fp32 [N, C_i])."""
+        heads = [getattr(self, n) for n in names]
+        if len(heads) == 1 or any(h.bias is None for h in heads) or any(h.kernel_volume != 1 for h in heads):
+            return [h(feat).F for h in heads]
+        from gcdlss_b200.functional import SparseConvFunction
+        from gcdlss_b200.config import get_math_mode
+        from gcdlss_b200 import ops
+        widths = [h.out_channels for h in heads]
+        total = sum(widths)
+        pad = (-total) % 16                       # the tensor-core path wants a multiple of 16 output channels
+        w = torch.cat([h.kernel for h in heads] + ([heads[0].kernel.new_zeros(heads[0].in_channels, pad)] if pad else []), 1)
+        b = torch.cat([h.bias for h in heads] + ([heads[0].bias.new_zeros(1, pad)] if pad else []), 1)
+        x = feat._F
+        kmap = feat.coordinate_manager.kernel_map(feat.tensor_stride_int, 1, 1, False)
+        if get_math_mode() == "bf16" and x.dtype != torch.bfloat16 and ops.tc_supported(x.shape[1], total + pad, 1):
+            x = x.to(torch.bfloat16)
+        out = SparseConvFunction.apply(x, w, b, kmap, torch.float32)
+        return list(torch.split(out[:, :total], widths, dim=1))
+
     def _ncc_logits(self, feat, reduce):
-        known = self.final(feat).F
-        return torch.cat([known, reduce(self.final2(feat).F)], dim=1)
+        known, rc = self._heads(feat, ("final", "final2"))
+        return torch.cat([known, reduce(rc)], dim=1)
 
     def forward_dummy(self, feat):
         return self._ncc_logits(feat, lambda t: torch.max(t, dim=1, keepdim=True)[0])
@@ -137,9 +160,8 @@ class MinkUNetBaseRC(_UNetTrunk):
         return self._ncc_logits(feat, lambda t: torch.sum(t, dim=1, keepdim=True))
 
     def forward_novel(self, feat):
-        known = self.final(feat).F
-        rc = torch.max(self.final2(feat).F, dim=1, keepdim=True)[0]
-        return torch.cat([known, self.final3(feat).F, rc], dim=1)
+        known, novel, rc = self._heads(feat, ("final", "final3", "final2"))
+        return torch.cat([known, novel, torch.max(rc, dim=1, keepdim=True)[0]], dim=1)
 
     def forward_dummy_sparse(self, x, is_seg=True):
         out = self.forward_no_logits(x)

@@ -96,6 +96,12 @@ int32_t gcd_quantize_f32(const float* pts, int64_t ld, int64_t n, int32_t dims, 
                          int32_t round_mode, int32_t* out, void* stream);
 int32_t gcd_quantize_f64(const double* pts, int64_t ld, int64_t n, int32_t dims, double q,
                          int32_t round_mode, int32_t* out, void* stream);
+/* Rigid / voxelisation transform of the dataset's augmentation step in float64, as numpy computes it from float32 points
+ * and a float64 4x4 matrix (ref utils/dataset_remission.py:821-833: homo_coords @ rigid_transformation.T[:, :3]):
+ *   out[i, j] = ((p[i,0]*m[j][0] + p[i,1]*m[j][1]) + p[i,2]*m[j][2]) + m[j][3]   (fused multiply-adds in that order)
+ * m_host: HOST pointer to the 12 doubles of the first three rows of the matrix (row-major).  out [n, 3] float64 feeds
+ * gcd_quantize_f64. */
+int32_t gcd_affine_f64(const float* pts, int64_t ld, int64_t n, const double* m_host, double* out, void* stream);
 /* Column-wise minimum of an int32 [n, dims] matrix (dims <= 4); mins must be pre-filled with
  * INT32_MAX.  Used for the `res_coors -= res_coors.min(0)` shift of models/voxelizer.py:276. */
 int32_t gcd_colmin_i32(const int32_t* coords, int64_t n, int32_t dims, int32_t* mins, void* stream);

@@ -130,3 +130,11 @@ def batched_coordinates(coords_list, dtype=np.int32) -> np.ndarray:
         out.append(np.concatenate([col, c.astype(dtype)], 1))
     D = np.asarray(coords_list[0]).shape[1] if len(coords_list) else 3
     return np.concatenate(out, 0) if out else np.zeros((0, 1 + D), dtype)
+
+
+def dataset_transform(points: np.ndarray, rigid_transformation: np.ndarray) -> np.ndarray:
+    """The augmentation transform of the reference's Dataset, verbatim (ref utils/dataset_remission.py:824-833): float32
+    points, homogeneous ones of the same dtype, a float64 4x4 matrix -> float64 [N, 3]."""
+    coordinates = points
+    homo_coords = np.hstack((coordinates, np.ones((coordinates.shape[0], 1), dtype=coordinates.dtype)))
+    return homo_coords @ rigid_transformation.T[:, :3]

@@ -77,6 +77,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
+    def wait_ready(self, timeout=5.0):
+        """Blocks until the sampler has delivered its first samples: nvidia-smi's start-up (NVML / driver initialisation,
+        ~0.5 s) disturbs kernel launches of this process while it lasts and must be over before anything is timed."""
+        t0 = time.perf_counter()
+        while self.proc is not None and len(self.lines) < 3 and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -398,6 +405,9 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("GCDLSS_BENCH_NO_CLOCKS"):       # (diagnosis only: the sampler is part of the contract)
         clocks.start()
+        clocks.wait_ready()
+    if world > 1:
+        dist.barrier()                    # the other ranks wait for rank 0's sampler too
     n_warm = warm_up(step_resident)
     import gc
     gc.collect()

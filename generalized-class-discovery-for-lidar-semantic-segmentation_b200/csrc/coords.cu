@@ -207,6 +207,55 @@ __global__ void __launch_bounds__(kThreads) kmap_subm_kernel(const int32_t* __re
     }
 }
 
+// Warp-cooperative probing (the design BASELINE.json's north_star names): a cooperative group of four lanes owns one output
+// voxel and probes the table one 32-byte SECTOR (four adjacent slots) at a time -- one coalesced load per probe, a ballot
+// inside the group for "found" / "chain ends here" -- instead of one thread walking its chain slot by slot.  Same table, same
+// result bit for bit as kmap_subm_kernel; selected by GCD_OPT_KMAP_COOP (measured against the other two searches in
+// profiles/).
+template <int K>
+__global__ void __launch_bounds__(kThreads) kmap_subm_coop_kernel(const int32_t* __restrict__ coords, int64_t n,
+                                                                   const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                                                                   int64_t cap, int ts, int32_t* __restrict__ nbr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t o = t >> 2;                         // four lanes per voxel
+  const int sub = threadIdx.x & 3;
+  const unsigned gmask = 0xFu << (threadIdx.x & 28);  // this group's lanes within the warp
+  if (o >= n) return;                               // n * 4 threads are launched in whole groups: a group leaves together
+  const int4 c = *reinterpret_cast<const int4*>(coords + o * 4);
+  constexpr int R = K / 2;
+#pragma unroll 1
+  for (int k = 0; k < K * K * K; ++k) {
+    const int kx = k % K, ky = (k / K) % K, kz = k / (K * K);
+    const int x = c.y + (kx - R) * ts, y = c.z + (ky - R) * ts, z = c.w + (kz - R) * ts;
+    int r = -1;
+    if (kx == R && ky == R && kz == R) r = (int)o;
+    else if (key_in_range(c.x, x, y, z)) {
+      const uint64_t key = pack_key(c.x, x, y, z);
+      const int64_t home = (int64_t)(hash_key(key) & (uint64_t)(cap - 1));
+      int64_t sector = home & ~int64_t(3);
+      unsigned live = 0xFu << (home & 3) & 0xFu;      // first sector: slots before the home slot are not on this key's chain
+      for (int64_t probes = 0; probes < cap; probes += 4) {
+        const int64_t slot = sector + sub;
+        const uint64_t cur = __ldg(&keys[slot]);
+        const unsigned hit = (__ballot_sync(gmask, cur == key) >> (threadIdx.x & 28)) & 0xFu;
+        const unsigned end = (__ballot_sync(gmask, cur == kEmptyKey) >> (threadIdx.x & 28)) & live;
+        if (hit) {
+          // a chain never skips an empty slot: a hit behind an empty slot of the live part would be a different chain's key,
+          // which cannot equal this key (keys are unique in the table) -- so any hit is the answer
+          const int src = (threadIdx.x & 28) + (__ffs(hit) - 1);
+          const int v = (cur == key) ? __ldg(&vals[slot]) : 0;
+          r = __shfl_sync(gmask, v, src);
+          break;
+        }
+        if (end) break;
+        sector = (sector + 4) & (cap - 1);
+        live = 0xFu;
+      }
+    }
+    if (sub == 0) nbr[(int64_t)k * n + o] = r;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = v;
@@ -393,8 +442,11 @@ extern "C" int32_t gcd_kmap_subm(const int32_t* coords, int64_t n, const uint64_
   GCD_REQUIRE(n >= 0 && ts >= 1, "gcd_kmap_subm: bad arguments");
   if (n == 0) return GCD_OK;
   cudaStream_t st = as_stream(stream);
-  if (kernel_size == 3) kmap_subm_kernel<3><<<grid_for(n), kThreads, 0, st>>>(coords, n, table_keys, table_vals, cap, ts, nbr);
-  else                  kmap_subm_kernel<5><<<grid_for(n), kThreads, 0, st>>>(coords, n, table_keys, table_vals, cap, ts, nbr);
+  if (option(GCD_OPT_KMAP_COOP)) {        // warp-cooperative probing: four lanes per voxel, one sector per probe
+    if (kernel_size == 3) kmap_subm_coop_kernel<3><<<grid_for(n * 4), kThreads, 0, st>>>(coords, n, table_keys, table_vals, cap, ts, nbr);
+    else                  kmap_subm_coop_kernel<5><<<grid_for(n * 4), kThreads, 0, st>>>(coords, n, table_keys, table_vals, cap, ts, nbr);
+  } else if (kernel_size == 3) kmap_subm_kernel<3><<<grid_for(n), kThreads, 0, st>>>(coords, n, table_keys, table_vals, cap, ts, nbr);
+  else                         kmap_subm_kernel<5><<<grid_for(n), kThreads, 0, st>>>(coords, n, table_keys, table_vals, cap, ts, nbr);
   GCD_LAUNCH_CHECK("gcd_kmap_subm");
   return GCD_OK;
 }

@@ -60,6 +60,15 @@ def new_batch():
     zeros_f32.new_period()
 
 
+def set_option(option: int, value: int) -> None:
+    """Process-wide tuning option of the library (``_cabi.OPT_*``; gcd_set_option)."""
+    call("gcd_set_option", int(option), int(value))
+
+
+def get_option(option: int) -> int:
+    return int(lib().gcd_get_option(int(option)))
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

@@ -86,7 +86,9 @@ typedef enum {
   GCD_OPT_TC_WARPS = 5,      /* 8 | 16: gather warps per CTA of the tcgen05 forward / dgrad kernel */
   GCD_OPT_BN_FUSED = 6,      /* 1 (default): the batch norms inside gcd_block_* run as one two-phase cooperative launch per
                                 direction (reduction, grid barrier, elementwise pass); 0: two launches */
-  GCD_OPT_COUNT_ = 7
+  GCD_OPT_KMAP_COOP = 7,     /* 1: gcd_kmap_subm probes warp-cooperatively (four lanes per voxel, one 32-byte sector per probe);
+                                0 (default): one thread per voxel.  Identical tables. */
+  GCD_OPT_COUNT_ = 8
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);

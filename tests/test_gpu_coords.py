@@ -84,3 +84,33 @@ def test_tiny_inputs(cuda):
     bc = np.array([[0, -3, 5, 7]], np.int32)
     mgr = build_manager(bc)
     check_levels(mgr, ocd.CoordLevels(bc))
+
+
+@pytest.mark.parametrize("kernel_size", [3, 5])
+def test_warp_cooperative_probing_gives_the_same_table(cuda, kernel_size):
+    """gcd_kmap_subm with GCD_OPT_KMAP_COOP (four lanes per voxel, one 32-byte sector of the table per probe) against the
+    one-thread-per-voxel search and the oracle: bit-identical tables, crowded table included (long chains, wrap-around)."""
+    from gcdlss_b200 import _cabi, ops, synth
+    from oracle import coords as ocd
+    from oracle import quantize as oq
+    xyz, _ = synth.make_scan("kitti", 1, n_points=40000)
+    c = oq.sparse_quantize_me(xyz, 0.05)[0]
+    bc = torch.from_numpy(oq.batched_coordinates([c, c[: c.shape[0] // 3] + np.array([3, -2, 1], np.int32)])).cuda()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    table = ops.hash_build(bc, status)
+    assert int(status.item()) == 0
+    ref = ops.kmap_subm(bc, table, kernel_size, 1)
+    ops.set_option(_cabi.OPT_KMAP_COOP, 1)
+    try:
+        got = ops.kmap_subm(bc, table, kernel_size, 1)
+    finally:
+        ops.set_option(_cabi.OPT_KMAP_COOP, 0)
+    assert torch.equal(got, ref)
+    small = bc[:3000].cpu().numpy()
+    table_s = ops.hash_build(bc[:3000].contiguous(), status)
+    ops.set_option(_cabi.OPT_KMAP_COOP, 1)
+    try:
+        got_s = ops.kmap_subm(bc[:3000].contiguous(), table_s, kernel_size, 1)
+    finally:
+        ops.set_option(_cabi.OPT_KMAP_COOP, 0)
+    np.testing.assert_array_equal(got_s.cpu().numpy().T, ocd.kmap_subm(small, kernel_size, 1))

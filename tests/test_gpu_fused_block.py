@@ -55,6 +55,12 @@ def _compare(a, b, mode):
         if k.startswith("d") and k.endswith("kernel"):        # fp32 atomics: order of accumulation differs run to run
             err = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-30))
             assert err < 1e-4, (k, err)
+        elif mode == "fp32" and k != "out":
+            # backward: the C-sequenced path runs the two-phase batch-norm kernel, the per-launch path the two stand-alone passes:
+            # the same source, but ptxas decides mul/add -> fma contraction per kernel, so fp32 values may differ in the last
+            # bit (bf16 storage rounds that away)
+            err = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-30))
+            assert err < 2e-6, (k, err)
         else:
             assert torch.equal(a[k], b[k]), (k, float((a[k] - b[k]).abs().max()))
 
@@ -138,7 +144,8 @@ def test_fused_path_is_taken(cuda):
         block(st)                                   # builds the kernel maps
         n0 = ops.launch_counter["calls"]
         block(st)
-        assert seen and ops.launch_counter["calls"] - n0 == 6
+        per_unit = 2 if ops.get_option(_cabi.OPT_BN_FUSED) else 3       # convolution + batch norm (one two-phase launch, or two)
+        assert seen and ops.launch_counter["calls"] - n0 == 2 * per_unit
     finally:
         _cabi._fn_cache["gcd_block_forward"] = orig
 

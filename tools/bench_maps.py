@@ -54,6 +54,12 @@ report("coords_stride2 (insert+scan+emit)", t, m * 16 + m * 8 + coarse.shape[0] 
 for K in (3, 5):
     t = timeit(lambda: ops.kmap_subm(bc, tb, K, 1), reps=10, flush=flush)
     report(f"kmap_subm_kernel<{K}>", t, m * 16 + K**3 * m * 8 + K**3 * m * 4)
+# warp-cooperative probing of the same point-wise table (GCD_OPT_KMAP_COOP: four lanes per voxel, one sector per probe)
+ops.set_option(_cabi.OPT_KMAP_COOP, 1)
+for K in (3, 5):
+    t = timeit(lambda: ops.kmap_subm(bc, tb, K, 1), reps=10, flush=flush)
+    report(f"kmap_subm_coop_kernel<{K}> (warp-coop)", t, m * 16 + K**3 * m * 8 + K**3 * m * 4)
+ops.set_option(_cabi.OPT_KMAP_COOP, 0)
 # the same tables searched in a run table (csrc/runtable.cuh, GCDLSS_KMAP=runs); same algorithmic bytes
 t = timeit(lambda: ops.runtable_build(bc, 1, status), flush=flush)
 rt = ops.runtable_build(bc, 1, status)

@@ -151,12 +151,13 @@ int main() {
 
   // ---- tile sort
   int32_t* d_sorted = dalloc<int32_t>((size_t)kv * n); int32_t* d_rows = dalloc<int32_t>(n);
+  uint32_t* d_masks = dalloc<uint32_t>((size_t)((n + 127) / 128));
   std::vector<int32_t> rows;
   {
     const size_t ws_bytes = gcd_tile_sort_workspace_bytes(n);
     void* ws; CK(cudaMalloc(&ws, ws_bytes));
-    GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, nullptr, ws, ws_bytes, nullptr));
-    const float t = time_ms([&] { GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, nullptr, ws, ws_bytes, nullptr)); });
+    GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, d_masks, ws, ws_bytes, nullptr));
+    const float t = time_ms([&] { GCD(gcd_kmap_tile_sort(d_nbr, n, kv, d_sorted, d_rows, d_masks, ws, ws_bytes, nullptr)); });
     rows = download(d_rows, n);
     std::vector<int32_t> sorted = download(d_sorted, (size_t)kv * n);
     std::vector<uint64_t> key(n, 0);
@@ -189,7 +190,7 @@ int main() {
     a.in = d_x; a.ld_in = c_in; a.n_in = n; a.nbr = d_nbr; a.kv = kv; a.n_out = n; a.c_in = c_in; a.c_out = c_out;
     a.w = d_w; a.w_packed = d_packed; a.w_stride_k = (int64_t)c_in * c_out; a.w_stride_c = c_out; a.w_stride_n = 1;
     a.out = d_y0; a.ld_out = c_out; a.in_dtype = GCD_BF16; a.out_dtype = GCD_BF16; a.math_mode = GCD_MATH_BF16_TCGEN05;
-    gcd_conv_args b = a; b.nbr = d_sorted; b.out_rows = d_rows; b.out = d_y1;
+    gcd_conv_args b = a; b.nbr = d_sorted; b.out_rows = d_rows; b.tile_masks = d_masks; b.out = d_y1;     // sorted table + per-tile offset masks
     GCD(gcd_conv_forward(&a, nullptr)); GCD(gcd_conv_forward(&b, nullptr));
     CK(cudaDeviceSynchronize());
     const float t0 = time_ms([&] { GCD(gcd_conv_forward(&a, nullptr)); });

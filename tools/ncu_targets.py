@@ -88,6 +88,12 @@ def coop():
 
 
 targets.append(coop)
+which = os.environ.get("NCU_TARGETS", "all")      # "conv": the tensor-core kernels + batch norm + tile sort; "side": hashing / maps / gather
+n_conv = 10
+if which == "conv":
+    targets = targets[:n_conv]
+elif which == "side":
+    targets = targets[n_conv:]
 for t in targets:            # warm-up: module loading, allocator
     t()
     t()

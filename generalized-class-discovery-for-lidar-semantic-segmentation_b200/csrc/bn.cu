@@ -305,6 +305,7 @@ __device__ __forceinline__ void column_reduce2_wide(int64_t n, int c, int rows_p
 
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bn_stats_wide_kernel(const T* __restrict__ x, int64_t ld, int64_t n, int c, int rows_per_block, double* __restrict__ stats) {
+  pdl_trigger(); pdl_wait();
   constexpr int V = VecW<T>::V;
   column_reduce2_wide<T, V, 4>(n, c, rows_per_block, stats, [&](int64_t r, int ch, float (&a)[V], float (&b)[V]) {
     VecW<T>::load(x + r * ld + ch, a);
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_reduce_wide_kernel(const T
                                                                           const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
                                                                           const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                                                                           int rows_per_block, double* __restrict__ sums) {
+  pdl_trigger(); pdl_wait();
   constexpr int V = VecW<T>::V;
   __shared__ float s_mean[kMaxChannels], s_is[kMaxChannels];
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) { s_mean[ch] = mean[ch]; s_is[ch] = invstd[ch]; }
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __r
                                                                      float* __restrict__ invstd_out, const float* __restrict__ scale_in,
                                                                      const float* __restrict__ shift_in, const T* __restrict__ res, int64_t ld_res,
                                                                      int relu, T* __restrict__ y, int64_t ld_y, int rows_per_block) {
+  pdl_trigger(); pdl_wait();
   bn_apply_wide_body<T, kTrain>(x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean_out, invstd_out, scale_in, shift_in,
                                 res, ld_res, relu, y, ld_y, rows_per_block);
 }
@@ -487,6 +490,7 @@ __global__ void __launch_bounds__(kVecThreads) bn_bwd_apply_wide_kernel(const T*
                                                                          const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
                                                                          int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
                                                                          int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
+  pdl_trigger(); pdl_wait();
   bn_bwd_apply_wide_body<T>(dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, dx, ld_dx, dres, ld_dres, dgamma, dbeta,
                             rows_per_block);
 }
@@ -503,6 +507,7 @@ struct BnFwdFusedArgs {
 };
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads) bn_fwd_fused_wide_kernel(const BnFwdFusedArgs a) {
+  pdl_trigger(); pdl_wait();
   constexpr int V = VecW<T>::V;
   const T* x = static_cast<const T*>(a.x);
   column_reduce2_wide<T, V, 4>(a.n, a.c, a.rows_per_block, a.stats, [&](int64_t r, int ch, float (&va)[V], float (&vb)[V]) {
@@ -523,6 +528,7 @@ struct BnBwdFusedArgs {
 };
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads, 3) bn_bwd_fused_wide_kernel(const BnBwdFusedArgs a) {
+  pdl_trigger(); pdl_wait();
   constexpr int V = VecW<T>::V;
   const T* dy = static_cast<const T*>(a.dy);
   const T* x = static_cast<const T*>(a.x);
@@ -850,14 +856,13 @@ int32_t bn_forward_train(const void* x, int64_t ld_x, int64_t n, int32_t c, doub
                          int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream) {
   if (n > 0 && option(GCD_OPT_BN_FUSED)) {
     BnFwdFusedArgs a{x, ld_x, n, c, stats, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, res, ld_res, relu, y, ld_y, 0};
-    void* params[] = {&a};
     cudaError_t e = cudaErrorInvalidValue;
     if (dtype == GCD_BF16 && wide_ok<__nv_bfloat16>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res}) && fwd_fused_occupancy<__nv_bfloat16>() > 0) {
       a.rows_per_block = fwd_partition_rows<__nv_bfloat16>(n, c);
-      e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+      e = launch_coop_pdl(bn_fwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
     } else if (dtype == GCD_F32 && wide_ok<float>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res}) && fwd_fused_occupancy<float>() > 0) {
       a.rows_per_block = fwd_partition_rows<float>(n, c);
-      e = cudaLaunchCooperativeKernel((void*)bn_fwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+      e = launch_coop_pdl(bn_fwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
     }
     if (e == cudaSuccess) return GCD_OK;
     cudaGetLastError();          // not applicable / not launchable here: the two-pass form below
@@ -874,16 +879,15 @@ int32_t bn_backward_train(const void* dy, int64_t ld_dy, const void* x, int64_t 
                           void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream) {
   if (n > 0 && option(GCD_OPT_BN_FUSED)) {
     BnBwdFusedArgs a{dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, dx, ld_dx, dres, ld_dres, dgamma, dbeta, 0};
-    void* params[] = {&a};
     cudaError_t e = cudaErrorInvalidValue;
     if (dtype == GCD_BF16 && wide_ok<__nv_bfloat16>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}) &&
         bwd_fused_occupancy<__nv_bfloat16>() > 0) {
       a.rows_per_block = bwd_partition_rows<__nv_bfloat16>(n, c);
-      e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+      e = launch_coop_pdl(bn_bwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
     } else if (dtype == GCD_F32 && wide_ok<float>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}) &&
                bwd_fused_occupancy<float>() > 0) {
       a.rows_per_block = bwd_partition_rows<float>(n, c);
-      e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), params, 0, as_stream(stream));
+      e = launch_coop_pdl(bn_bwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
     }
     if (e == cudaSuccess) return GCD_OK;
     cudaGetLastError();
@@ -902,12 +906,12 @@ extern "C" int32_t gcd_bn_stats(const void* x, int64_t ld, int64_t n, int32_t c,
   dim3 block(kRedX, kRedY);
   if (dtype == GCD_F32) {
     using T = float;
-    if (wide_ok<T>(c, {ld}, {x})) { const int rows = gcd::fwd_partition_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
+    if (wide_ok<T>(c, {ld}, {x})) { const int rows = gcd::fwd_partition_rows<T>(n, c); launch_pdl(bn_stats_wide_kernel<T>, dim3(rows_grid(n, rows)), dim3(kVecThreads), 0, st, (const T*)x, ld, n, c, rows, stats); }
     else if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
     else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
   } else {
     using T = __nv_bfloat16;
-    if (wide_ok<T>(c, {ld}, {x})) { const int rows = gcd::fwd_partition_rows<T>(n, c); bn_stats_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)x, ld, n, c, rows, stats); }
+    if (wide_ok<T>(c, {ld}, {x})) { const int rows = gcd::fwd_partition_rows<T>(n, c); launch_pdl(bn_stats_wide_kernel<T>, dim3(rows_grid(n, rows)), dim3(kVecThreads), 0, st, (const T*)x, ld, n, c, rows, stats); }
     else if (vec_shape_ok(c) && vec_ok<T>(c, {ld}, {x})) bn_stats_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)x, ld, n, c, red_rows(n), stats);
     else bn_stats_kernel<T><<<reduce_grid(n), block, 0, st>>>((const T*)x, ld, n, c, stats);
   }
@@ -939,8 +943,8 @@ void launch_apply(bool train, const void* x, int64_t ld_x, int64_t n, int c, con
   if (wide_ok<T>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res})) {
     const int rows = wide_rows<T>(n, c);
     const unsigned g = rows_grid(n, rows);
-    if (train) bn_apply_wide_kernel<T, true><<<g, kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, nullptr, nullptr, (const T*)res, ld_res, relu, (T*)y, ld_y, rows);
-    else bn_apply_wide_kernel<T, false><<<g, kVecThreads, 0, st>>>((const T*)x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, (const T*)res, ld_res, relu, (T*)y, ld_y, rows);
+    if (train) launch_pdl(bn_apply_wide_kernel<T, true>, dim3(g), dim3(kVecThreads), 0, st, (const T*)x, ld_x, n, c, stats, gamma, beta, eps, momentum, rm, rv, mean, invstd, nullptr, nullptr, (const T*)res, ld_res, relu, (T*)y, ld_y, rows);
+    else launch_pdl(bn_apply_wide_kernel<T, false>, dim3(g), dim3(kVecThreads), 0, st, (const T*)x, ld_x, n, c, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, scale, shift, (const T*)res, ld_res, relu, (T*)y, ld_y, rows);
     return;
   }
   const bool vec = vec_ok<T>(c, {ld_x, ld_y, res ? ld_res : 0}, {x, y, res});
@@ -994,7 +998,7 @@ extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const v
     using T = float;
     if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr})) {
       const int rows = gcd::bwd_partition_rows<T>(n, c);      // the partition of the fused two-phase form: both paths sum the same partials
-      bn_bwd_reduce_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
+      launch_pdl(bn_bwd_reduce_wide_kernel<T>, dim3(rows_grid(n, rows)), dim3(kVecThreads), 0, st, (const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
     } else if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
       bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
     else
@@ -1003,7 +1007,7 @@ extern "C" int32_t gcd_bn_backward_reduce(const void* dy, int64_t ld_dy, const v
     using T = __nv_bfloat16;
     if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr})) {
       const int rows = gcd::bwd_partition_rows<T>(n, c);      // the partition of the fused two-phase form: both paths sum the same partials
-      bn_bwd_reduce_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
+      launch_pdl(bn_bwd_reduce_wide_kernel<T>, dim3(rows_grid(n, rows)), dim3(kVecThreads), 0, st, (const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, rows, sums);
     } else if (vec_shape_ok(c) && vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0}, {dy, x, relu ? y : nullptr}))
       bn_bwd_reduce_vec_kernel<T><<<red_grid(n), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, relu, red_rows(n), sums);
     else
@@ -1020,7 +1024,7 @@ void launch_bwd_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x
                       int64_t ld_dx, void* dres, int64_t ld_dres, float* dgamma, float* dbeta, cudaStream_t st) {
   if (wide_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres})) {
     const int rows = wide_rows<T>(n, c);
-    bn_bwd_apply_wide_kernel<T><<<rows_grid(n, rows), kVecThreads, 0, st>>>((const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta, rows);
+    launch_pdl(bn_bwd_apply_wide_kernel<T>, dim3(rows_grid(n, rows)), dim3(kVecThreads), 0, st, (const T*)dy, ld_dy, (const T*)x, ld_x, (const T*)y, ld_y, n, c, mean, invstd, gamma, sums, relu, training, (T*)dx, ld_dx, (T*)dres, ld_dres, dgamma, dbeta, rows);
     return;
   }
   const bool vec = vec_ok<T>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres});

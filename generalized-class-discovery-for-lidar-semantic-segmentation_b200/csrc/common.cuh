@@ -36,6 +36,50 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the training step starts with pdl_trigger() (its successor in the
+// stream may be launched as soon as all of this grid's blocks are resident) and executes pdl_wait() before it first touches
+// global memory that a predecessor may still be writing or reading: block scheduling, barrier / TMEM set-up and parameter
+// loads of kernel i + 1 overlap the tail of kernel i instead of following it (a MinkUNet34 step is ~350 dependent launches
+// on one stream).  Without the launch attribute both instructions are no-ops, so the same kernels run under plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute when GCD_OPT_PDL is on.
+// ONLY for kernels that call pdl_wait() before their first global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = option(GCD_OPT_PDL) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// cooperative launch (grid-wide barrier inside the kernel), with the PDL attribute when the driver accepts the combination
+template <typename Arg>
+inline cudaError_t launch_coop_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, cudaStream_t st, const Arg& a) {
+  static int pdl_ok = 1;      // benign race: worst case the combination is tried twice
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  if (pdl_ok && option(GCD_OPT_PDL)) {
+    cfg.numAttrs = 2;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();
+    pdl_ok = 0;
+  }
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 // Open-addressing table, linear probing.  Slots are grouped in 32-byte sectors of four keys; a
 // probe sequence visits whole sectors so the four keys a DRAM/L2 sector delivers are all used.
 // insert: returns the slot holding `key` (claimed or already present), or -1 when the table is full.

@@ -46,6 +46,7 @@ constexpr int kTileRing = 32;               // published iteration counts (the M
 constexpr int kSliceBytes = kTileM * 4;     // one offset's [128] slice of the neighbour table
 constexpr int kRingSlices = 56;             // shared-memory ring of table slices: two whole 3x3x3 tiles, ~6 tiles of a sorted table
 constexpr int kTableSlots = 8;              // tiles the table warp may run ahead (barriers / masks per slot)
+constexpr int kDynAhead = 4;                // ... under a dynamic tile schedule
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // TMEM columns between the two accumulator buffers
 constexpr int kSmemBudget = 226 * 1024;
@@ -63,6 +64,7 @@ struct FwdParams {
   int group;                       // producer warps that share one stage (1, 2, 4, 8)
   const int32_t* out_rows;         // kPerm kernels: output row of table column i (tile-sorted table, tilesort.cu)
   const uint32_t* tile_masks;      // optional: offsets with a hit per 128-column tile of nbr (tilesort.cu); the table warp then stages only those slices
+  int32_t* sched;                  // optional: {next tile, finished CTAs}, zero on entry and on exit: tiles are claimed dynamically (see below)
 #ifdef GCD_TC_PROFILE
   long long* dbg;
   int ablate;                      // profile build only: 1 = no MMA issue, 2 = no gather copies, 4 = weight copies of 16 B
@@ -109,17 +111,37 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
   uint32_t* s_mask = s_tmem_base + 1;           // [kTableSlots] offsets with at least one hit in the slot's tile
   uint32_t* s_base = s_mask + kTableSlots;      // [kTableSlots] ring position of the tile's first slice, bit 31: slices are compacted (mask order)
   int32_t* s_iters = reinterpret_cast<int32_t*>(s_base + kTableSlots);  // [kTileRing]
+  int32_t* s_work = s_iters + kTileRing;        // [kTileRing] dynamic schedule: the tile claimed for each sequence number, -1 = no more work
+  uint32_t* s_pub = reinterpret_cast<uint32_t*>(s_work + kTileRing);    // dynamic schedule: number of entries of s_work published so far
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();                   // the next kernel of the stream may be scheduled; it waits for this grid before it reads or writes
   const int S = p.stages;
   const int nq = kNQ ? kNQ : (p.c_in + kChunkK - 1) / kChunkK;
   const int last_width = p.c_in - (nq - 1) * kChunkK;      // channels of the last slice (multiple of 16)
   const int64_t tiles_m = (p.n_out + kTileM - 1) / kTileM;
   const int64_t n_work = tiles_m * p.n_tiles_n;
-  const uint32_t rot = (blockIdx.x * 11u) % (uint32_t)p.kv;   // per-CTA rotation of the offset order (spreads weight reads)
+  // Tile schedule.  Static (p.sched == NULL): CTA b takes tiles b, b + grid, ...  Dynamic: the table warp claims the next tile
+  // from a global counter and hands its index to the other roles through s_work, heaviest tiles first (a tile-sorted table
+  // keeps the rows with many neighbours at its end).  A CTA that becomes resident late -- another kernel (NCCL, a weight
+  // gradient on a second stream) holds its SM -- then finds little or nothing left instead of running its fixed share as a
+  // second wave, and tiles of very different cost (1 .. 27 offsets in a sorted table) balance themselves.
+  const bool dyn = p.sched != nullptr;
+  auto static_work = [&](uint32_t seq) -> int64_t {
+    const int64_t w = (int64_t)blockIdx.x + (int64_t)seq * gridDim.x;
+    return w < n_work ? w : -1;
+  };
+  // other roles: wait until the table warp has published entry `seq` (warp-uniform result)
+  auto published_work = [&](uint32_t seq) -> int64_t {
+    const uint32_t addr = smem_u32(s_pub);
+    uint32_t pub;
+    do { pub = ld_acquire_shared_u32(addr); } while (!__all_sync(0xffffffffu, pub > seq));
+    return (int64_t)s_work[seq & (kTileRing - 1)];
+  };
 
   if (threadIdx.x == 0) {
     // full: one completion-triggered arrival per lane of the owning producer warp + its lane 0's arrive.expect_tx (weights)
+    *s_pub = 0;
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 32 * p.group + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     // ready: one completion-triggered arrival per lane of the table warp (its cp.async copies) + lane 0's plain arrive
@@ -131,9 +153,10 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_base;
+  pdl_wait();                      // everything above overlapped the previous kernel's tail; from here on global memory is touched
 
   // order in which a tile's active offsets are visited (shared by the gather warps and the weight warp)
-  auto rotate = [&](uint32_t mask, uint32_t& hi, uint32_t& lo) {
+  auto rotate = [&](uint32_t mask, uint32_t rot, uint32_t& hi, uint32_t& lo) {
     if (mask == 0) mask = 1;                   // degenerate tile: run offset 0 with all-zero rows
     lo = mask & ((1u << rot) - 1u);
     hi = mask & ~((1u << rot) - 1u);
@@ -171,19 +194,29 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
 #ifdef GCD_TC_PROFILE
     long long prof_wait = 0, prof_iters = 0, prof_table = 0; const long long prof_t0 = clock64();
 #endif
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+    for (;; ++tile_seq) {
 #ifdef GCD_TC_PROFILE
       const long long ct0 = clock64();
 #endif
       // the table warp stages the slice one tile ahead: no producer-wide synchronisation at tile boundaries, a warp
       // that has issued its last stage of tile t goes straight on to its first stage of tile t + 1
       const uint32_t tb = tile_seq % kTableSlots;
-      mbar_wait(&table_ready[tb], (tile_seq / kTableSlots) & 1);
+      int64_t work;
+      if (dyn) {
+        mbar_wait(&table_ready[tb], (tile_seq / kTableSlots) & 1);      // also orders the read of s_work after its publication
+        work = s_work[tile_seq & (kTileRing - 1)];
+      } else {
+        work = static_work(tile_seq);
+      }
+      if (work < 0) break;
+      if (!dyn) mbar_wait(&table_ready[tb], (tile_seq / kTableSlots) & 1);
       const uint32_t s_nbr_addr = smem_u32(s_nbr0);
       const uint32_t tile_mask = s_mask[tb], tile_base = s_base[tb] & 0x7fffffffu;
       const bool compact = (s_base[tb] >> 31) != 0;
       uint32_t mask = tile_mask, lo_mask;
-      rotate(mask, mask, lo_mask);
+      // per-tile rotation of the offset order (spreads the CTAs' weight reads over the slices; a function of the tile, not of the
+      // CTA, so that a tile's summation order does not depend on which CTA claims it)
+      rotate(mask, (uint32_t)((work / p.n_tiles_n) * 11) % (uint32_t)p.kv, mask, lo_mask);
       const uint8_t* w_tile = p.w_packed + (int64_t)(work % p.n_tiles_n) * p.n_tile_cols * kRowBytes;
 #ifdef GCD_TC_PROFILE
       prof_table += clock64() - ct0;
@@ -259,22 +292,50 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
     const bool compact = p.tile_masks != nullptr;
     const bool aligned = (p.n_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0;
     uint32_t next_mask = 0;
-    if (compact && (int64_t)blockIdx.x < n_work) next_mask = __ldg(&p.tile_masks[blockIdx.x / p.n_tiles_n]);
+    // dynamic schedule: ticket t of the global counter is tile (tiles_m - 1 - t / n_tiles_n, t % n_tiles_n); one ticket is
+    // held ahead so that the tile's offset mask is in flight while the previous tile is staged
+    auto claim = [&]() -> int64_t {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(p.sched, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if ((int64_t)t >= n_work) return -1;
+      return (tiles_m - 1 - t / p.n_tiles_n) * p.n_tiles_n + t % p.n_tiles_n;
+    };
+    int64_t next_work = dyn ? claim() : static_work(0);
+    if (compact && next_work >= 0) next_mask = __ldg(&p.tile_masks[next_work / p.n_tiles_n]);
+    const uint32_t max_ahead = dyn ? (uint32_t)kDynAhead : (uint32_t)kTableSlots;
 #ifdef GCD_TC_PROFILE
     long long prof_twait = 0; const long long prof_t0 = clock64();
 #endif
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+    for (;; ++tile_seq) {
+      const int64_t work = next_work;
+      if (work < 0 && !dyn) break;
       const uint32_t tb = tile_seq % kTableSlots;
+      if (work < 0) {
+        // end of the dynamic schedule: publish the sentinel through the slot protocol (the gather warps wait on table_ready)
+        while (tile_seq - tail_seq >= (uint32_t)kTableSlots) {
+          mbar_wait(&table_free[tail_seq % kTableSlots], (tail_seq / kTableSlots) & 1);
+          ++tail_seq;
+        }
+        if (lane == 0) s_work[tile_seq & (kTileRing - 1)] = -1;
+        __syncwarp();
+        cp_async_mbar_arrive_noinc(&table_ready[tb]);
+        mbar_arrive_pred(&table_ready[tb], lane == 0 ? 1u : 0u);
+        if (lane == 0) st_release_shared_u32(smem_u32(s_pub), tile_seq + 1);
+        break;
+      }
       const int64_t row0 = (work / p.n_tiles_n) * kTileM;
       uint32_t mask = next_mask;
-      if (compact && work + gridDim.x < n_work) next_mask = __ldg(&p.tile_masks[(work + gridDim.x) / p.n_tiles_n]);   // one tile ahead
+      next_work = dyn ? claim() : static_work(tile_seq + 1);
+      if (compact && next_work >= 0) next_mask = __ldg(&p.tile_masks[next_work / p.n_tiles_n]);   // one tile ahead
       const uint32_t load_mask = mask ? mask : 1u;         // degenerate tile: offset 0 runs with all-zero rows
       const uint32_t n_sl = compact ? (uint32_t)__popc(load_mask) : (uint32_t)p.kv;
 #ifdef GCD_TC_PROFILE
       const long long ctw0 = clock64();
 #endif
-      // room in the ring and a free slot: release the oldest tiles the gather warps are done with
-      while (used + n_sl > (uint32_t)kRingSlices || tile_seq - tail_seq >= (uint32_t)kTableSlots) {
+      // room in the ring and a free slot: release the oldest tiles the gather warps are done with (a dynamic schedule runs
+      // fewer tiles ahead: what is claimed early is work another CTA cannot take at the end of the launch)
+      while (used + n_sl > (uint32_t)kRingSlices || tile_seq - tail_seq >= max_ahead) {
         const uint32_t ts = tail_seq % kTableSlots;
         mbar_wait(&table_free[ts], (tail_seq / kTableSlots) & 1);
         used -= (uint32_t)(counts >> (6 * ts)) & 63u;
@@ -335,16 +396,24 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
         s_mask[tb] = mask;
         s_base[tb] = base | (compact ? 0x80000000u : 0u);
         s_iters[tile_seq & (kTileRing - 1)] = __popc(mask ? mask : 1u) * nq;
+        s_work[tile_seq & (kTileRing - 1)] = (int32_t)work;
       }
       __syncwarp();
       cp_async_mbar_arrive_noinc(&table_ready[tb]);        // each lane: arrives once its copies of this tile have landed
       mbar_arrive_pred(&table_ready[tb], lane == 0 ? 1u : 0u);
+      if (dyn && lane == 0) st_release_shared_u32(smem_u32(s_pub), tile_seq + 1);   // MMA / epilogue warps: entry tile_seq is readable
       head = base + n_sl;
       if (head >= (uint32_t)kRingSlices) head -= kRingSlices;
       used += n_sl;
       counts = (counts & ~(63ull << (6 * tb))) | ((unsigned long long)n_sl << (6 * tb));
     }
     cp_async_wait_all();
+    if (dyn && lane == 0) {
+      // every CTA takes exactly one ticket beyond the work: when the last one has, nobody claims again and the counters go
+      // back to zero for the next launch on this stream
+      __threadfence();
+      if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
+    }
 #ifdef GCD_TC_PROFILE
     if (p.dbg && lane == 0) { long long* d = p.dbg + (int64_t)blockIdx.x * 16; d[8] = clock64() - prof_t0; d[9] = prof_twait; }
 #endif
@@ -365,7 +434,8 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
 #ifdef GCD_TC_PROFILE
     long long prof_full = 0, prof_acc = 0; const long long prof_t0 = clock64();
 #endif
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+    for (;; ++tile_seq) {
+      if ((dyn ? published_work(tile_seq) : static_work(tile_seq)) < 0) break;
       const uint32_t buf = tile_seq & 1;
 #ifdef GCD_TC_PROFILE
       const long long ca0 = clock64();
@@ -417,7 +487,9 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
 #ifdef GCD_TC_PROFILE
     long long prof_ewait = 0; const long long prof_t0 = clock64();
 #endif
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++tile_seq) {
+    for (;; ++tile_seq) {
+      const int64_t work = dyn ? published_work(tile_seq) : static_work(tile_seq);
+      if (work < 0) break;
       const int64_t tm = work / p.n_tiles_n;
       const int tn = (int)(work - tm * p.n_tiles_n);
       const uint32_t buf = tile_seq & 1;
@@ -545,7 +617,10 @@ struct WgParams {
   int chunk;            // pairs per work item (multiple of 64)
   float* dw;
   int stages;
+  int32_t* sched;       // optional {next item, finished CTAs}: dynamic schedule as in the forward kernel (warp 13 is the scheduler)
 };
+constexpr int kWgRing = 16;          // published work items (ring)
+constexpr int kWgAhead = 6;          // items the scheduler may run ahead of the epilogue
 
 template <int kGS>   // kGS = number of 64-channel slabs of the output gradient (ceil(c_out / 64), 1..4)
 __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgParams p) {
@@ -560,27 +635,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* s_tmem_base = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   int32_t* s_cum = reinterpret_cast<int32_t*>(s_tmem_base + 4);        // [kv + 1] cumulative chunk counts
+  int32_t* s_work = s_cum + kWgMaxOffsets + 1;                         // [kWgRing] dynamic schedule: claimed items, -1 = no more work
+  uint32_t* s_pub = reinterpret_cast<uint32_t*>(s_work + kWgRing);     // entries of s_work published so far
+  uint32_t* s_done = s_pub + 1;                                        // items the epilogue has finished
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
+    *s_pub = 0; *s_done = 0;
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpilogueThreads / 32); }
     fence_mbar_init();
-    int cum = 0;
-    for (int k = 0; k < p.kv; ++k) {
-      s_cum[k] = cum;
-      const int64_t nk = p.pair_off ? (int64_t)p.pair_off[k + 1] - p.pair_off[k] : p.n_rows_identity;
-      cum += (int)((nk + p.chunk - 1) / p.chunk);
-    }
-    s_cum[p.kv] = cum;
   }
   if (warp == kMmaWarp) { tmem_alloc<kTmemCols>(s_tmem_base); tmem_relinquish(); }
+  pdl_wait();                      // barrier / TMEM set-up above overlaps the previous kernel's tail; global memory from here on
+  // chunk counts per offset: one parallel round of loads, then a prefix sum in shared memory (a serial loop of kv dependent
+  // global loads used to open every launch)
+  if ((int)threadIdx.x < p.kv) {
+    const int64_t nk = p.pair_off ? (int64_t)__ldg(&p.pair_off[threadIdx.x + 1]) - __ldg(&p.pair_off[threadIdx.x]) : p.n_rows_identity;
+    s_cum[threadIdx.x + 1] = (int)((nk + p.chunk - 1) / p.chunk);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_cum[0] = 0;
+    for (int k = 0; k < p.kv; ++k) s_cum[k + 1] += s_cum[k];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_base;
   const int64_t n_work = (int64_t)s_cum[p.kv] * p.m_tiles;
+  const bool dyn = p.sched != nullptr;
+  // item `seq` of this CTA: static striding, or whatever the scheduler warp claimed (see conv_fwd_tc_kernel)
+  auto get_work = [&](uint32_t seq) -> int64_t {
+    if (!dyn) {
+      const int64_t w = (int64_t)blockIdx.x + (int64_t)seq * gridDim.x;
+      return w < n_work ? w : -1;
+    }
+    const uint32_t addr = smem_u32(s_pub);
+    uint32_t pub;
+    do { pub = ld_acquire_shared_u32(addr); } while (!__all_sync(0xffffffffu, pub > seq));
+    return (int64_t)s_work[seq & (kWgRing - 1)];
+  };
 
   // work -> (k, first pair, last pair, m tile)
   auto decode = [&](int64_t work, int& k, int64_t& p_begin, int64_t& p_end, int& mt) {
@@ -613,7 +710,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
     const int PA = S < kProducerWarps ? S : kProducerWarps;
     uint32_t st = warp, ph = 0;
     int64_t own_skip = warp < PA ? warp : (int64_t)1 << 60;                  // stages until this warp's next owned one
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+    for (uint32_t seq = 0;; ++seq) {
+      const int64_t work = get_work(seq);
+      if (work < 0) break;
       int k, mt; int64_t p_begin, p_end;
       decode(work, k, p_begin, p_end, mt);
       const int64_t n_stages = (p_end - p_begin + kWgPairs - 1) / kWgPairs;
@@ -672,7 +771,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
       const bool leader = elect_one();
       uint32_t st = 0, ph = 0, seq = 0;
       uint32_t da = da0_lo, db = db0_lo;
-      for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++seq) {
+      for (;; ++seq) {
+        const int64_t work = get_work(seq);
+        if (work < 0) break;
         int k, mt; int64_t p_begin, p_end;
         decode(work, k, p_begin, p_end, mt);
         const uint32_t buf = seq & 1;
@@ -700,7 +801,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
     // ===================================================================== epilogue (warps 8-11; warp 13 idles here)
     const int ew = warp - kEpilogueWarp0;
     uint32_t seq = 0;
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, ++seq) {
+    for (;; ++seq) {
+      const int64_t work = get_work(seq);
+      if (work < 0) break;
       int k, mt; int64_t p_begin, p_end;
       decode(work, k, p_begin, p_end, mt);
       const uint32_t buf = seq & 1;
@@ -722,6 +825,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (dyn && ew == 0 && lane == 0) st_release_shared_u32(smem_u32(s_done), seq + 1);     // back-pressure for the scheduler
+    }
+  } else if (dyn) {
+    // ===================================================================== scheduler (warp 13, dynamic schedule only)
+    for (uint32_t seq = 0;; ++seq) {
+      uint32_t done;
+      do { done = ld_acquire_shared_u32(smem_u32(s_done)); } while (!__all_sync(0xffffffffu, seq - done < (uint32_t)kWgAhead));
+      int t = 0;
+      if (lane == 0) t = atomicAdd(p.sched, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      const int32_t work = (int64_t)t < n_work ? t : -1;
+      if (lane == 0) {
+        s_work[seq & (kWgRing - 1)] = work;
+        st_release_shared_u32(smem_u32(s_pub), seq + 1);
+      }
+      if (work < 0) break;
+    }
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
     }
   }
 
@@ -746,6 +869,7 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   p.in = (const __nv_bfloat16*)a->in; p.ld_in = a->ld_in; p.gout = (const __nv_bfloat16*)a->gout; p.ld_g = a->ld_gout;
   p.pair_in = a->pair_in; p.pair_out = a->pair_out; p.pair_off = a->pair_off; p.n_rows_identity = a->n_pairs;
   p.kv = a->kv; p.c_in = a->c_in; p.c_out = a->c_out; p.dw = a->dw;
+  p.sched = a->sched;
   GCD_REQUIRE(a->ld_in > 0 && a->ld_in < (int64_t(1) << 31) && a->ld_gout > 0 && a->ld_gout < (int64_t(1) << 31), "conv_wgrad_tc: row pitch out of range");
   p.m_tiles = (a->c_in + 127) / 128;
   p.g_slabs = (a->c_out + 63) / 64;
@@ -769,8 +893,7 @@ int32_t conv_wgrad_tc(const gcd_wgrad_args* a, cudaStream_t st) {
   if (const cudaError_t e = tc_kernels_opt_in(); e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcgen05 kernels)");
   const int64_t work_bound = (ceil_div(a->n_pairs, chunk) + a->kv) * p.m_tiles;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(work_bound, kNumSMs));
-  kernels[p.g_slabs - 1]<<<grid, kTcThreads, smem, st>>>(p);
-  GCD_LAUNCH_CHECK("gcd_conv_wgrad(tcgen05)");
+  if (const cudaError_t e = launch_pdl(kernels[p.g_slabs - 1], dim3(grid), dim3(kTcThreads), smem, st, p); e != cudaSuccess) return cuda_fail(e, "gcd_conv_wgrad(tcgen05)");
   return GCD_OK;
 }
 
@@ -839,6 +962,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.bias = a->bias; p.out = a->out; p.ld_out = a->ld_out; p.out_is_bf16 = a->out_dtype == GCD_BF16;
   p.out_rows = a->out_rows;
   p.tile_masks = a->tile_masks;
+  p.sched = a->sched;
   GCD_REQUIRE(a->out_rows == nullptr || a->nbr != nullptr, "conv_forward_tc: out_rows needs a neighbour table");
   GCD_REQUIRE(a->tile_masks == nullptr || a->nbr != nullptr, "conv_forward_tc: tile_masks needs a neighbour table");
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;
@@ -864,8 +988,7 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   if (a->c_in > 16 * kChunkK) { set_error("conv_forward_tc: more than 1024 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;
   const unsigned grid = (unsigned)std::min<int64_t>(n_work, kNumSMs);
-  kernel<<<grid, (pw + 6) * 32, smem, st>>>(p);
-  GCD_LAUNCH_CHECK("gcd_conv_forward(tcgen05)");
+  if (const cudaError_t e = launch_pdl(kernel, dim3(grid), dim3((pw + 6) * 32), smem, st, p); e != cudaSuccess) return cuda_fail(e, "gcd_conv_forward(tcgen05)");
   return GCD_OK;
 }
 }  // namespace gcd

@@ -78,6 +78,16 @@ __device__ __forceinline__ int lds_s32(uint32_t smem_addr) {
   return v;
 }
 
+// release / acquire on a shared-memory word (CTA scope): a role publishes a counter after the data it guards
+__device__ __forceinline__ void st_release_shared_u32(uint32_t smem_addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared_u32(uint32_t smem_addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- async copies
 // 16-byte cp.async (LDGSTS) with zero fill: src_bytes = 16 copies, 0 writes zeros.
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {

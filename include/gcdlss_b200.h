@@ -88,7 +88,15 @@ typedef enum {
                                 direction (reduction, grid barrier, elementwise pass); 0: two launches */
   GCD_OPT_KMAP_COOP = 7,     /* 1: gcd_kmap_subm probes warp-cooperatively (four lanes per voxel, one 32-byte sector per probe);
                                 0 (default): one thread per voxel.  Identical tables. */
-  GCD_OPT_COUNT_ = 8
+  GCD_OPT_PDL = 8,           /* 1 (default): the kernels of the training step (convolutions, batch norms, adds / copies) are
+                                launched with programmatic stream serialization: kernel i + 1 is scheduled and runs its set-up
+                                while kernel i drains, and waits (griddepcontrol.wait) before touching global memory; 0: plain
+                                launches.  Results are identical. */
+  GCD_OPT_WGRAD_SIDE = 9,    /* gcd_run_ops_exec: 1 (default) weight gradients on the context's second stream, ordered after the
+                                block's batch-norm backward (they may run beside the input-gradient kernel); 2: ordered after the
+                                input-gradient kernel; 0: everything on the caller's stream */
+  GCD_OPT_DYN_TILES = 10,    /* gcd_run_ops_exec: 1 (default) dynamic tile schedule of the tcgen05 kernels; 0: static striding */
+  GCD_OPT_COUNT_ = 11
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);
@@ -216,6 +224,10 @@ typedef struct {
                               result of table column i is written to row out_rows[i] of out; NULL = row i */
   const uint32_t* tile_masks; /* optional (tcgen05 path only): per 128-column tile of nbr, the mask of offsets with a hit
                                  (gcd_kmap_tile_sort); NULL = the kernel derives it from the whole table slice */
+  int32_t* sched;          /* optional (tcgen05 path only): two device int32, ZERO on entry and zero again when the kernel has
+                              finished: the CTAs claim row tiles from this counter (heaviest first) instead of striding over
+                              them, so a CTA that starts late because another kernel holds its SM steals no one's time.  One
+                              pair per stream in flight (launches of one stream may share it); NULL = static striding */
 } gcd_conv_args;
 
 int32_t gcd_conv_forward(const gcd_conv_args* args, void* stream);
@@ -241,6 +253,7 @@ typedef struct {
   float* dbias;                         /* optional [c_out]: += column sums of gout (caller zeroes) */
   int64_t n_out;                        /* rows of gout (for dbias) */
   int32_t in_dtype, gout_dtype, math_mode;
+  int32_t* sched;                       /* optional (tcgen05 path): as gcd_conv_args.sched, for the kernel's work items */
 } gcd_wgrad_args;
 
 int32_t gcd_conv_wgrad(const gcd_wgrad_args* args, void* stream);
@@ -393,6 +406,16 @@ typedef struct {
   int32_t reserved;
 } gcd_op;
 int32_t gcd_run_ops(gcd_op* ops, int32_t n_ops, void* stream, int32_t* launches);
+
+/* The same with an execution context (caller-owned; use one per stream, from one host thread at a time):
+ *   - the tcgen05 kernels claim their tiles dynamically (gcd_conv_args.sched; the context owns the counters);
+ *   - in backward blocks the weight-gradient kernels, which feed nothing but the optimiser, are issued on the context's second
+ *     stream behind an event and joined at the end of the call: they fill the SMs the gradient chain leaves idle (the deep
+ *     levels of a U-Net have fewer row tiles than SMs) and the tails of its persistent kernels (GCD_OPT_WGRAD_SIDE).
+ * Results are those of gcd_run_ops (weight gradients are accumulated with atomics in both). */
+int32_t gcd_exec_create(void** exec);
+int32_t gcd_exec_destroy(void* exec);
+int32_t gcd_run_ops_exec(void* exec, gcd_op* ops, int32_t n_ops, void* stream, int32_t* launches);
 
 #ifdef __cplusplus
 }

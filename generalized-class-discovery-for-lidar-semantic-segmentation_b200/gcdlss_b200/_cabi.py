@@ -19,7 +19,7 @@ F32, BF16 = 0, 1
 MATH_FP32_SIMT, MATH_BF16_TC = 0, 1
 ROUND_FLOOR, ROUND_HALF_EVEN = 0, 1
 DEV_KEY_RANGE, DEV_DUPLICATE, DEV_TABLE_FULL = 1, 2, 4
-OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN, OPT_TC_WARPS, OPT_BN_FUSED, OPT_KMAP_COOP, OPT_PDL = range(9)
+OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN, OPT_TC_WARPS, OPT_BN_FUSED, OPT_KMAP_COOP, OPT_PDL, OPT_WGRAD_SIDE, OPT_DYN_TILES = range(11)
 
 
 def build(force: bool = False) -> str:
@@ -59,7 +59,7 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64),
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
         ("stats", C.c_void_p), ("math_mode", C.c_int32),
-        ("out_rows", C.c_void_p), ("tile_masks", C.c_void_p),
+        ("out_rows", C.c_void_p), ("tile_masks", C.c_void_p), ("sched", C.c_void_p),
     ]
 
 
@@ -72,6 +72,7 @@ class WgradArgs(C.Structure):
         ("kv", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32),
         ("dw", C.c_void_p), ("dbias", C.c_void_p), ("n_out", C.c_int64),
         ("in_dtype", C.c_int32), ("gout_dtype", C.c_int32), ("math_mode", C.c_int32),
+        ("sched", C.c_void_p),
     ]
 
 
@@ -172,6 +173,9 @@ PROTOTYPES = {
     "gcd_block_forward": (_i32, [C.POINTER(BlockArgs), _vp]),
     "gcd_block_backward": (_i32, [C.POINTER(BlockArgs), _vp]),
     "gcd_run_ops": (_i32, [C.POINTER(Op), _i32, _vp, C.POINTER(_i32)]),
+    "gcd_exec_create": (_i32, [C.POINTER(_vp)]),
+    "gcd_exec_destroy": (_i32, [_vp]),
+    "gcd_run_ops_exec": (_i32, [_vp, C.POINTER(Op), _i32, _vp, C.POINTER(_i32)]),
     "gcd_segment_reduce": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
 }
 

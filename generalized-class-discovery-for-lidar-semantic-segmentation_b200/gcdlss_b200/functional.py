@@ -647,9 +647,7 @@ class TrunkFunction(torch.autograd.Function):
                 cur, off, c_cur = residual(blk, k3, k1, cur, ld, n)
                 ld = c_cur
             outs.append((off, n, c_cur))
-        launches = C.c_int32(0)
-        call("gcd_run_ops", prog, n_ops, ops._stream(), C.byref(launches))
-        ops._count(launches.value)
+        ops.run_ops(prog, n_ops, backward=False)
         ctx.plan, ctx.blocks_c, ctx.sizes, ctx.n_lv, ctx.x_dtype, ctx.x_shape = plan, blocks_c, sizes, n_lv, x.dtype, tuple(xd.shape)
         # everything the structs point into: input, arena, statistics, the kernel maps (tables, pair lists) of every level
         ctx.keep = (xd, act, moments, [mgr.kernel_map(*k) for k in list(mgr._kmaps)])
@@ -778,8 +776,7 @@ class TrunkFunction(torch.autograd.Function):
         if need_dx and -1 in skip_extra:
             ptr, ld_src = skip_extra[-1]
             add_cols(blocks_c[0].dx, 0 or blocks_c[0].u1.c_in, ptr, ld_src, blocks_c[0].u1.n_in, blocks_c[0].u1.c_in)
-        call("gcd_run_ops", prog, n_ops, ops._stream(), C.byref(launches))
-        ops._count(launches.value)
+        ops.run_ops(prog, n_ops, backward=True)
         dx = None
         if need_dx:
             dx = garena.view(dx_first[0], dx_first[1], dx_first[2], dt)

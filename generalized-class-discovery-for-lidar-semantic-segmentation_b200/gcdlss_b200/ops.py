@@ -69,6 +69,42 @@ def get_option(option: int) -> int:
     return int(lib().gcd_get_option(int(option)))
 
 
+class _ExecContexts:
+    """Execution contexts of the library (gcd_exec_create: a second stream for the weight gradients of a backward pass,
+    the events that order it, the counters of the dynamic tile schedule), one per (device, stream) the trunk runs on.
+    Created on first use, destroyed with the process (a context may only be used from one host thread at a time: the
+    autograd engine runs the backward of one device on one thread, the forward on the caller's)."""
+
+    def __init__(self):
+        self._ctx = {}
+
+    def get(self, stream_ptr: int, backward: bool) -> C.c_void_p:
+        key = (_cur_device(), int(stream_ptr), backward)
+        h = self._ctx.get(key)
+        if h is None:
+            out = C.c_void_p(0)
+            call("gcd_exec_create", C.byref(out))
+            h = self._ctx[key] = out
+        return h
+
+    def close(self):
+        for h in self._ctx.values():
+            lib().gcd_exec_destroy(h)
+        self._ctx.clear()
+
+
+exec_contexts = _ExecContexts()
+
+
+def run_ops(prog, n_ops: int, backward: bool) -> int:
+    """gcd_run_ops_exec on the current stream with that stream's execution context; returns the number of kernels launched."""
+    launches = C.c_int32(0)
+    st = _stream()
+    call("gcd_run_ops_exec", exec_contexts.get(st, backward), prog, n_ops, st, C.byref(launches))
+    _count(launches.value)
+    return launches.value
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -344,12 +380,13 @@ def pack_weights_batched(desc_table_dev: torch.Tensor, n_descs: int, total_block
 
 
 def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, bias=None, out_dtype=None, math_mode=MATH_FP32_SIMT,
-                 w_packed=None, stats=None, out_rows=None, tile_masks=None):
+                 w_packed=None, stats=None, out_rows=None, tile_masks=None, sched=None):
     """out[o] = sum_k inp[nbr[k, o]] @ B_k, B_k = w3[k] (or w3[wsel(k)]^T when transpose_w).
 
     inp [n_in, c_in'] row-major; nbr [kv, n_out] int32 or None (identity); w3 fp32 [kv, c_in, c_out].
     ``out_rows`` (tcgen05 path only): ``nbr`` is a tile-sorted table (:func:`kmap_tile_sort`) and column i of it is
-    output row out_rows[i]; ``tile_masks``: its per-tile offset masks.
+    output row out_rows[i]; ``tile_masks``: its per-tile offset masks; ``sched``: two zero int32 on the device, the
+    kernel then claims its row tiles dynamically (gcd_conv_args.sched) and leaves the counters zero again.
     """
     _require_cuda(inp, w3)
     inp = _rowmajor(inp)
@@ -377,6 +414,7 @@ def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, b
     a.math_mode = math_mode
     a.out_rows = out_rows.data_ptr() if out_rows is not None else None
     a.tile_masks = tile_masks.data_ptr() if tile_masks is not None else None
+    a.sched = sched.data_ptr() if sched is not None else None
     kind = "conv_tc" if math_mode == MATH_BF16_TC else "conv_simt"
     end = kernel_timer.bracket(kind, nbr, n_out, kv, k_dim, n_dim)
     call("gcd_conv_forward", C.byref(a), _stream())
@@ -389,7 +427,7 @@ def conv_forward(inp, nbr, w3, n_out: int, *, transpose_w=False, mirror=False, b
     return out
 
 
-def conv_wgrad(inp, gout, pairs, kv: int, dw: torch.Tensor, dbias=None, math_mode=MATH_FP32_SIMT):
+def conv_wgrad(inp, gout, pairs, kv: int, dw: torch.Tensor, dbias=None, math_mode=MATH_FP32_SIMT, sched=None):
     """dw[k] += inp[pair_in]^T gout[pair_out] (accumulating); pairs = (pair_in, pair_out, pair_off) or None (identity)."""
     _require_cuda(inp, gout, dw)
     inp, gout = _rowmajor(inp), _rowmajor(gout)
@@ -408,6 +446,7 @@ def conv_wgrad(inp, gout, pairs, kv: int, dw: torch.Tensor, dbias=None, math_mod
     a.n_out = gout.shape[0]
     a.in_dtype, a.gout_dtype = _dtype_code(inp), _dtype_code(gout)
     a.math_mode = math_mode
+    a.sched = sched.data_ptr() if sched is not None else None
     kind = "wgrad_tc" if math_mode == MATH_BF16_TC else "wgrad_simt"
     end = kernel_timer.bracket(kind, pairs[0] if pairs is not None else None, gout.shape[0], kv, inp.shape[1], gout.shape[1])
     call("gcd_conv_wgrad", C.byref(a), _stream())

@@ -58,9 +58,10 @@ def test_struct_layout_matches_c():
     a = _cabi.ConvArgs
     assert (a.inp.offset, a.nbr.offset, a.kv.offset, a.n_out.offset, a.c_in.offset, a.w.offset) == (0, 24, 32, 40, 48, 56)
     assert (a.mirror.offset, a.bias.offset, a.out.offset, a.in_dtype.offset, a.stats.offset, a.math_mode.offset) == (96, 104, 112, 128, 136, 144)
-    assert (a.out_rows.offset, a.tile_masks.offset) == (152, 160) and ctypes.sizeof(a) == 168
+    assert (a.out_rows.offset, a.tile_masks.offset, a.sched.offset) == (152, 160, 168) and ctypes.sizeof(a) == 176
     w = _cabi.WgradArgs
     assert (w.pair_in.offset, w.n_pairs.offset, w.kv.offset, w.dw.offset, w.n_out.offset, w.math_mode.offset) == (32, 56, 64, 80, 96, 112)
+    assert w.sched.offset == 120 and ctypes.sizeof(w) == 128
 
 
 def test_block_struct_layout_against_gcc(tmp_path):

@@ -215,6 +215,7 @@ def run_ours(args):
     import gcdlss_b200
     import MinkowskiEngine as ME
     from gcdlss_b200 import ops, synth
+    from gcdlss_b200.config import nvtx_range
     from gcdlss_b200.ddp import GradBucketReducer
     from gcdlss_b200.steps import point_cross_entropy
     from models.multiheadminkunet import MinkUNetBase
@@ -286,12 +287,17 @@ def run_ours(args):
             opt.zero_grad(set_to_none=True)        # gradients are taken over from the wgrad kernels' buffers, no accumulate pass
         else:
             reducer.reset()                        # .grad are views of the flat all-reduce buckets: zero them in place
-        out = model(st)
-        loss = point_cross_entropy(out["logits"], labels)
-        loss.backward()
+        with nvtx_range("step:forward"):
+            out = model(st)
+        with nvtx_range("step:loss"):
+            loss = point_cross_entropy(out["logits"], labels)
+        with nvtx_range("step:backward"):
+            loss.backward()
         if reducer is not None:
-            reducer.finish()
-        opt.step()
+            with nvtx_range("step:gradient all-reduce (wait)"):
+                reducer.finish()
+        with nvtx_range("step:optimizer"):
+            opt.step()
         return loss
 
     # Both loops are software-pipelined by one batch: while step i trains on the main stream, batch i+1 is prepared on

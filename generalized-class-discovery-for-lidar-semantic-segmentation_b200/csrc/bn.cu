@@ -258,7 +258,19 @@ struct ItemWalk {
     step_g = kVecThreads % groups; step_r = kVecThreads / groups;
   }
   __device__ __forceinline__ void next() { g += step_g; r += step_r; if (g >= groups) { g -= groups; ++r; } }
+  // the same items backwards (two-phase kernels: the elementwise pass starts with the rows the reduction read last, which
+  // are the ones still in the L2 when the layer's operands do not fit it): position on this thread's k-th item
+  __device__ __forceinline__ void seek(int64_t row0, int64_t k) {
+    const int64_t item = (int64_t)threadIdx.x + k * kVecThreads;
+    r = row0 + item / groups; g = (int)(item % groups);
+  }
+  __device__ __forceinline__ void prev() { g -= step_g; r -= step_r; if (g < 0) { g += groups; --r; } }
 };
+// number of items thread t walks in a block of `rows` rows
+__device__ __forceinline__ int64_t items_of_thread(int64_t rows, int groups) {
+  const int64_t n_items = rows * groups;
+  return n_items > (int64_t)threadIdx.x ? (n_items - 1 - threadIdx.x) / kVecThreads + 1 : 0;
+}
 
 template <typename T, int V, int U, typename F>
 __device__ __forceinline__ void column_reduce2_wide(int64_t n, int c, int rows_per_block, double* __restrict__ sums, F f) {
@@ -377,9 +389,13 @@ __device__ __forceinline__ void bn_apply_wide_body(const T* __restrict__ x, int6
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t row_end = min(row0 + rows_per_block, n);
   ItemWalk a(c / V, row0);
-  while (a.r < row_end) {
-    ItemWalk b = a; b.next();
-    const bool two = b.r < row_end;
+  // kCoherent (two-phase kernel): walk backwards, most recently read rows first
+  int64_t left = kCoherent ? items_of_thread(row_end > row0 ? row_end - row0 : 0, c / V) : 0;
+  if (kCoherent && left > 0) a.seek(row0, left - 1);
+  while (kCoherent ? left > 0 : a.r < row_end) {
+    ItemWalk b = a;
+    if (kCoherent) b.prev(); else b.next();
+    const bool two = kCoherent ? left > 1 : b.r < row_end;
     float va[V], vb[V], ra[V], rb[V];
     VecW<T>::load(x + a.r * ld_x + a.g * V, va);
     if (two) VecW<T>::load(x + b.r * ld_x + b.g * V, vb);
@@ -403,7 +419,8 @@ __device__ __forceinline__ void bn_apply_wide_body(const T* __restrict__ x, int6
       }
       VecW<T>::store(y + b.r * ld_y + b.g * V, vb);
     }
-    a = b; a.next();
+    a = b;
+    if (kCoherent) { a.prev(); left -= 2; } else a.next();
   }
 }
 
@@ -447,9 +464,12 @@ __device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy,
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t row_end = min(row0 + rows_per_block, n);
   ItemWalk a(c / V, row0);
-  while (a.r < row_end) {
-    ItemWalk b = a; b.next();
-    const bool two = b.r < row_end;
+  int64_t left = kCoherent ? items_of_thread(row_end > row0 ? row_end - row0 : 0, c / V) : 0;      // two-phase kernel: backwards (see ItemWalk::seek)
+  if (kCoherent && left > 0) a.seek(row0, left - 1);
+  while (kCoherent ? left > 0 : a.r < row_end) {
+    ItemWalk b = a;
+    if (kCoherent) b.prev(); else b.next();
+    const bool two = kCoherent ? left > 1 : b.r < row_end;
     float ga[V], gb[V], xa[V], xb[V], ya[V], yb[V], o[V];
     VecW<T>::load(dy + a.r * ld_dy + a.g * V, ga);
     VecW<T>::load(x + a.r * ld_x + a.g * V, xa);
@@ -479,7 +499,8 @@ __device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy,
       VecW<T>::store(dx + b.r * ld_dx + b.g * V, o);
       if (dres) VecW<T>::store(dres + b.r * ld_dres + b.g * V, gb);
     }
-    a = b; a.next();
+    a = b;
+    if (kCoherent) { a.prev(); left -= 2; } else a.next();
   }
 }
 

@@ -65,6 +65,8 @@ struct FwdParams {
   const int32_t* out_rows;         // kPerm kernels: output row of table column i (tile-sorted table, tilesort.cu)
   const uint32_t* tile_masks;      // optional: offsets with a hit per 128-column tile of nbr (tilesort.cu); the table warp then stages only those slices
   int32_t* sched;                  // optional: {next tile, finished CTAs}, zero on entry and on exit: tiles are claimed dynamically (see below)
+  int dyn_ascending;               // dynamic schedule: 1 = tickets map to tiles in table order, 0 = last (heaviest, in a sorted table) tile first
+  int dyn_ahead;                   // dynamic schedule: tiles the table warp may claim ahead of the gather warps (1 .. kTableSlots)
 #ifdef GCD_TC_PROFILE
   long long* dbg;
   int ablate;                      // profile build only: 1 = no MMA issue, 2 = no gather copies, 4 = weight copies of 16 B
@@ -299,11 +301,12 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
       if (lane == 0) t = atomicAdd(p.sched, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if ((int64_t)t >= n_work) return -1;
-      return (tiles_m - 1 - t / p.n_tiles_n) * p.n_tiles_n + t % p.n_tiles_n;
+      const int64_t tm = t / p.n_tiles_n;
+      return (p.dyn_ascending ? tm : tiles_m - 1 - tm) * p.n_tiles_n + t % p.n_tiles_n;
     };
     int64_t next_work = dyn ? claim() : static_work(0);
     if (compact && next_work >= 0) next_mask = __ldg(&p.tile_masks[next_work / p.n_tiles_n]);
-    const uint32_t max_ahead = dyn ? (uint32_t)kDynAhead : (uint32_t)kTableSlots;
+    const uint32_t max_ahead = dyn ? (uint32_t)p.dyn_ahead : (uint32_t)kTableSlots;
 #ifdef GCD_TC_PROFILE
     long long prof_twait = 0; const long long prof_t0 = clock64();
 #endif
@@ -963,6 +966,8 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   p.out_rows = a->out_rows;
   p.tile_masks = a->tile_masks;
   p.sched = a->sched;
+  p.dyn_ascending = option(GCD_OPT_DYN_TILES) == 2;
+  p.dyn_ahead = std::max(1, std::min(kTableSlots, option(GCD_OPT_DYN_AHEAD) > 0 ? option(GCD_OPT_DYN_AHEAD) : kDynAhead));
   GCD_REQUIRE(a->out_rows == nullptr || a->nbr != nullptr, "conv_forward_tc: out_rows needs a neighbour table");
   GCD_REQUIRE(a->tile_masks == nullptr || a->nbr != nullptr, "conv_forward_tc: tile_masks needs a neighbour table");
   const int stage_bytes = kABytes + p.n_tile_cols * kRowBytes;

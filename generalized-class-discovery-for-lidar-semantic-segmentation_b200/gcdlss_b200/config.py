@@ -63,3 +63,34 @@ def get_tile_sort() -> bool:
 
 def tile_sort_min_rows() -> int:
     return _state["tile_sort_min_rows"]
+
+
+# NVTX ranges around the phases of a step (map build on the prefetch stream, trunk forward / backward, loss, gradient exchange,
+# optimiser): off by default (a range costs two driver calls), on with GCDLSS_NVTX=1 or set_nvtx(True) for nsys / ncu --nvtx
+# timelines.  (the reference has no tracing of its own; this is the hook a profiler run needs.)
+_state["nvtx"] = os.environ.get("GCDLSS_NVTX", "0") not in ("0", "")
+
+
+def set_nvtx(enabled: bool) -> None:
+    _state["nvtx"] = bool(enabled)
+
+
+class nvtx_range:
+    """``with nvtx_range("name"):`` -- an NVTX range when tracing is on, nothing otherwise."""
+
+    __slots__ = ("name", "on")
+
+    def __init__(self, name: str):
+        self.name, self.on = name, _state["nvtx"]
+
+    def __enter__(self):
+        if self.on:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False

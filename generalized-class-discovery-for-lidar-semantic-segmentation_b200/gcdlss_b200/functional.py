@@ -13,7 +13,7 @@ import ctypes as C
 
 from . import ops
 from ._cabi import MATH_BF16_TC, MATH_FP32_SIMT, BlockArgs, call
-from .config import get_math_mode
+from .config import get_math_mode, nvtx_range
 
 class PackedWeights:
     """bf16 tcgen05 operand images (forward and dgrad orientation) of every convolution module, kept in
@@ -647,7 +647,8 @@ class TrunkFunction(torch.autograd.Function):
                 cur, off, c_cur = residual(blk, k3, k1, cur, ld, n)
                 ld = c_cur
             outs.append((off, n, c_cur))
-        ops.run_ops(prog, n_ops, backward=False)
+        with nvtx_range("gcd:trunk forward"):
+            ops.run_ops(prog, n_ops, backward=False)
         ctx.plan, ctx.blocks_c, ctx.sizes, ctx.n_lv, ctx.x_dtype, ctx.x_shape = plan, blocks_c, sizes, n_lv, x.dtype, tuple(xd.shape)
         # everything the structs point into: input, arena, statistics, the kernel maps (tables, pair lists) of every level
         ctx.keep = (xd, act, moments, [mgr.kernel_map(*k) for k in list(mgr._kmaps)])
@@ -776,7 +777,8 @@ class TrunkFunction(torch.autograd.Function):
         if need_dx and -1 in skip_extra:
             ptr, ld_src = skip_extra[-1]
             add_cols(blocks_c[0].dx, 0 or blocks_c[0].u1.c_in, ptr, ld_src, blocks_c[0].u1.n_in, blocks_c[0].u1.c_in)
-        ops.run_ops(prog, n_ops, backward=True)
+        with nvtx_range("gcd:trunk backward"):
+            ops.run_ops(prog, n_ops, backward=True)
         dx = None
         if need_dx:
             dx = garena.view(dx_first[0], dx_first[1], dx_first[2], dt)

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 
+from .config import nvtx_range
 from .sparse_tensor import SparseTensor
 
 
@@ -41,7 +42,7 @@ class BatchPrefetcher:
         are produced by work already queued on the current stream."""
         if wait_for_current_stream:
             self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.stream), nvtx_range("gcd:prefetch (inputs, hash, kernel maps, tile sort)"):
             feats, coords, extras = make_inputs()
             st = SparseTensor(features=feats, coordinates=coords)
             st.coordinate_manager.prebuild_unet(self.n_levels, self.stem_kernel, with_pairs=self.training)

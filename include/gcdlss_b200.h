@@ -95,8 +95,10 @@ typedef enum {
   GCD_OPT_WGRAD_SIDE = 9,    /* gcd_run_ops_exec: 1 (default) weight gradients on the context's second stream, ordered after the
                                 block's batch-norm backward (they may run beside the input-gradient kernel); 2: ordered after the
                                 input-gradient kernel; 0: everything on the caller's stream */
-  GCD_OPT_DYN_TILES = 10,    /* gcd_run_ops_exec: 1 (default) dynamic tile schedule of the tcgen05 kernels; 0: static striding */
-  GCD_OPT_COUNT_ = 11
+  GCD_OPT_DYN_TILES = 10,    /* gcd_run_ops_exec: 1: dynamic tile schedule of the tcgen05 kernels (heaviest tiles first); 2: the same in
+                                table order; 0 (default): static striding (measured faster on an otherwise idle GPU, r2 call 9) */
+  GCD_OPT_DYN_AHEAD = 11,    /* > 0: tiles a CTA of the forward / dgrad kernel may claim ahead under the dynamic schedule (1..8, tuning aid) */
+  GCD_OPT_COUNT_ = 12
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);

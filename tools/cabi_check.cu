@@ -129,11 +129,11 @@ int main() {
     CK(cudaFree(d_n5a)); CK(cudaFree(d_n5b));
   }
 
-  // ---- pair lists
+  // ---- pair lists (kept for the weight-gradient check below)
+  int32_t* d_pi = dalloc<int32_t>((size_t)kv * n); int32_t* d_po = dalloc<int32_t>((size_t)kv * n); int32_t* d_off = dalloc<int32_t>(kv + 1);
   {
     const size_t ws_bytes = gcd_pairs_workspace_bytes(n, kv);
     void* ws; CK(cudaMalloc(&ws, ws_bytes));
-    int32_t* d_pi = dalloc<int32_t>((size_t)kv * n); int32_t* d_po = dalloc<int32_t>((size_t)kv * n); int32_t* d_off = dalloc<int32_t>(kv + 1);
     GCD(gcd_pairs_from_table(d_nbr, n, kv, d_pi, d_po, d_off, ws, ws_bytes, nullptr));
     const float t = time_ms([&] { GCD(gcd_pairs_from_table(d_nbr, n, kv, d_pi, d_po, d_off, ws, ws_bytes, nullptr)); });
     std::vector<int32_t> off = download(d_off, kv + 1), ref_off(kv + 1), ref_in, ref_out;
@@ -146,7 +146,7 @@ int main() {
     if (ok) ok = download(d_pi, ref_in.size()) == ref_in && download(d_po, ref_out.size()) == ref_out;
     snprintf(buf, sizeof buf, "%zu pairs, %.1f us", ref_in.size(), t * 1e3);
     report("pair lists == host", ok, buf);
-    CK(cudaFree(ws)); CK(cudaFree(d_pi)); CK(cudaFree(d_po)); CK(cudaFree(d_off));
+    CK(cudaFree(ws));
   }
 
   // ---- tile sort
@@ -218,6 +218,49 @@ int main() {
     snprintf(buf, sizeof buf, "%d->%d: %.1f us scan order, %.1f us sorted; rel err vs host %.2e / %.2e, sorted vs scan %.2e", c_in, c_out, t0 * 1e3, t1 * 1e3,
              err0 / max_ref, err1 / max_ref, diff / max_y);
     report("conv through the tile-sorted table == scan-order conv", err0 / max_ref < 3e-2 && err1 / max_ref < 3e-2 && diff / max_y < 3e-2, buf);
+    {
+      // dynamic tile schedule (gcd_conv_args.sched): the same bits whichever CTA claims a tile, counters zero afterwards
+      int32_t* d_sched = dalloc<int32_t>(2); CK(cudaMemset(d_sched, 0, 8));
+      __nv_bfloat16* d_y2 = dalloc<__nv_bfloat16>((size_t)n * c_out);
+      gcd_conv_args d = b; d.out = d_y2; d.sched = d_sched;
+      GCD(gcd_conv_forward(&d, nullptr)); GCD(gcd_conv_forward(&d, nullptr));
+      const float t2 = time_ms([&] { GCD(gcd_conv_forward(&d, nullptr)); });
+      std::vector<__nv_bfloat16> y2 = download(d_y2, (size_t)n * c_out);
+      std::vector<int32_t> sc = download(d_sched, 2);
+      snprintf(buf, sizeof buf, "%d->%d: %.1f us dynamic vs %.1f us static", c_in, c_out, t2 * 1e3, t1 * 1e3);
+      report("dynamic tile schedule == static striding (bit-exact), counters reset", memcmp(y2.data(), y1.data(), y1.size() * 2) == 0 && sc[0] == 0 && sc[1] == 0, buf);
+      // weight gradient over the pair lists, static and dynamic schedule, against the host on sampled entries
+      std::vector<__nv_bfloat16> gy((size_t)n * c_out);
+      std::vector<float> gf(gy.size());
+      for (size_t i = 0; i < gy.size(); ++i) { gy[i] = __float2bfloat16(gauss(rng)); gf[i] = __bfloat162float(gy[i]); }
+      __nv_bfloat16* d_g = upload(gy);
+      float* d_dw0 = dalloc<float>(w.size()); float* d_dw1 = dalloc<float>(w.size());
+      CK(cudaMemset(d_dw0, 0, w.size() * 4)); CK(cudaMemset(d_dw1, 0, w.size() * 4));
+      gcd_wgrad_args g; memset(&g, 0, sizeof g);
+      g.in = d_x; g.ld_in = c_in; g.gout = d_g; g.ld_gout = c_out; g.pair_in = d_pi; g.pair_out = d_po; g.pair_off = d_off;
+      g.n_pairs = (int64_t)kv * n; g.kv = kv; g.c_in = c_in; g.c_out = c_out; g.dw = d_dw0; g.n_out = n;
+      g.in_dtype = GCD_BF16; g.gout_dtype = GCD_BF16; g.math_mode = GCD_MATH_BF16_TCGEN05;
+      GCD(gcd_conv_wgrad(&g, nullptr));
+      gcd_wgrad_args gd = g; gd.dw = d_dw1; gd.sched = d_sched;
+      GCD(gcd_conv_wgrad(&gd, nullptr));
+      std::vector<float> dw0 = download(d_dw0, w.size()), dw1 = download(d_dw1, w.size());
+      sc = download(d_sched, 2);
+      double werr = 0, wmax = 0, wdiff = 0;
+      for (size_t i = 0; i < dw0.size(); ++i) wdiff = std::max(wdiff, (double)std::fabs(dw0[i] - dw1[i]));
+      for (int s = 0; s < 40; ++s) {
+        const int k = (int)(uni(rng) * kv) % kv, ci = (int)(uni(rng) * c_in) % c_in, co = (int)(uni(rng) * c_out) % c_out;
+        double acc = 0;
+        for (int64_t o = 0; o < n; ++o) {
+          const int32_t i = nbr[(size_t)k * n + o];
+          if (i >= 0) acc += (double)xf[(size_t)i * c_in + ci] * (double)gf[(size_t)o * c_out + co];
+        }
+        wmax = std::max(wmax, std::fabs(acc));
+        werr = std::max(werr, std::fabs(acc - dw0[((size_t)k * c_in + ci) * c_out + co]));
+      }
+      snprintf(buf, sizeof buf, "%d->%d: rel err vs host %.2e, dynamic vs static %.2e (abs)", c_in, c_out, werr / wmax, wdiff);
+      report("weight gradient (tcgen05, pair lists) == host, dynamic == static", werr / wmax < 1e-3 && wdiff < 1e-2 * wmax && sc[0] == 0 && sc[1] == 0, buf);
+      CK(cudaFree(d_sched)); CK(cudaFree(d_y2)); CK(cudaFree(d_g)); CK(cudaFree(d_dw0)); CK(cudaFree(d_dw1));
+    }
     CK(cudaFree(d_x)); CK(cudaFree(d_w)); CK(cudaFree(d_packed)); CK(cudaFree(d_y0)); CK(cudaFree(d_y1));
   }
 

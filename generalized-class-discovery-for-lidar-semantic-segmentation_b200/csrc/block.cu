@@ -329,6 +329,21 @@ int32_t run_ops(Exec* ex, gcd_op* ops, int32_t n_ops, void* stream, int32_t* lau
         rc = cols_op(o, true, as_stream(stream));
         ++total;
         break;
+      case GCD_OP_RECORD_EVENT: {
+        // everything issued so far by this call -- on the caller's stream and on the context's side stream -- precedes the event
+        cudaEvent_t ev = reinterpret_cast<cudaEvent_t>(o->dst);
+        if (ev == nullptr) { set_error("gcd_run_ops: operation %d has no event", i); rc = GCD_ERR_INVALID_ARG; break; }
+        cudaError_t e;
+        if (ex && ex->side_used) {
+          e = cudaEventRecord(ex->fork, as_stream(stream));
+          if (e == cudaSuccess) e = cudaStreamWaitEvent(ex->side, ex->fork, 0);
+          if (e == cudaSuccess) e = cudaEventRecord(ev, ex->side);
+        } else {
+          e = cudaEventRecord(ev, as_stream(stream));
+        }
+        if (e != cudaSuccess) rc = cuda_fail(e, "gcd_run_ops(record event)");
+        break;
+      }
       default:
         set_error("gcd_run_ops: unknown operation %d at index %d", o->op, i);
         rc = GCD_ERR_INVALID_ARG;

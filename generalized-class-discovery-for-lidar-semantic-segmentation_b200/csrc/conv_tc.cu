@@ -296,15 +296,20 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
     uint32_t next_mask = 0;
     // dynamic schedule: ticket t of the global counter is tile (tiles_m - 1 - t / n_tiles_n, t % n_tiles_n); one ticket is
     // held ahead so that the tile's offset mask is in flight while the previous tile is staged
+    // position L of the schedule -> tile.  A CTA's first tile is position blockIdx.x (no atomic in front of the launch's first
+    // loads); ticket t of the counter is position gridDim.x + t.
+    auto tile_at = [&](int64_t pos) -> int64_t {
+      if (pos >= n_work) return -1;
+      const int64_t tm = pos / p.n_tiles_n;
+      return (p.dyn_ascending ? tm : tiles_m - 1 - tm) * p.n_tiles_n + pos % p.n_tiles_n;
+    };
     auto claim = [&]() -> int64_t {
       int t = 0;
       if (lane == 0) t = atomicAdd(p.sched, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
-      if ((int64_t)t >= n_work) return -1;
-      const int64_t tm = t / p.n_tiles_n;
-      return (p.dyn_ascending ? tm : tiles_m - 1 - tm) * p.n_tiles_n + t % p.n_tiles_n;
+      return tile_at((int64_t)gridDim.x + t);
     };
-    int64_t next_work = dyn ? claim() : static_work(0);
+    int64_t next_work = dyn ? tile_at(blockIdx.x) : static_work(0);
     if (compact && next_work >= 0) next_mask = __ldg(&p.tile_masks[next_work / p.n_tiles_n]);
     const uint32_t max_ahead = dyn ? (uint32_t)p.dyn_ahead : (uint32_t)kTableSlots;
 #ifdef GCD_TC_PROFILE
@@ -835,10 +840,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_wgrad_tc_kernel(const WgPa
     for (uint32_t seq = 0;; ++seq) {
       uint32_t done;
       do { done = ld_acquire_shared_u32(smem_u32(s_done)); } while (!__all_sync(0xffffffffu, seq - done < (uint32_t)kWgAhead));
-      int t = 0;
-      if (lane == 0) t = atomicAdd(p.sched, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      const int32_t work = (int64_t)t < n_work ? t : -1;
+      int64_t pos = blockIdx.x;                 // first item: static (no atomic in front of the launch's first loads)
+      if (seq > 0) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(p.sched, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        pos = (int64_t)gridDim.x + t;
+      }
+      const int32_t work = pos < n_work ? (int32_t)pos : -1;
       if (lane == 0) {
         s_work[seq & (kWgRing - 1)] = work;
         st_release_shared_u32(smem_u32(s_pub), seq + 1);

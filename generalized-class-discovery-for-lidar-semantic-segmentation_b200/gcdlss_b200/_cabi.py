@@ -106,7 +106,7 @@ class BlockArgs(C.Structure):
     ]
 
 
-OP_BLOCK_FORWARD, OP_BLOCK_BACKWARD, OP_COPY_COLS, OP_ADD_COLS = range(4)
+OP_BLOCK_FORWARD, OP_BLOCK_BACKWARD, OP_COPY_COLS, OP_ADD_COLS, OP_RECORD_EVENT = range(5)
 
 
 class Op(C.Structure):

@@ -44,6 +44,20 @@ class GradBucketReducer:
             self._close(cur)
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._on_grad_ready)
+        # Gradient sink (CUDA, more than one rank): the trunk's backward pass accumulates straight into the buckets and reports
+        # per network stage which parameters are final, with an event recorded behind the stage's kernels
+        # (functional.TrunkFunction.backward); a bucket whose last gradient arrives that way is all-reduced behind that event
+        # on a gate stream, i.e. while the rest of the backward pass is still running, instead of behind everything queued so far.
+        import os
+        self.direct = os.environ.get("GCDLSS_DDP_DIRECT", "1") not in ("0", "")      # A/B switch for the gradient sink
+        self._gate = {}              # bucket -> (sequence number, event) of the latest stage that touched it
+        self._stage_events = {}
+        self._seq = 0
+        self._gate_stream = None
+        if self.world > 1 and self.params and self.params[0].is_cuda:
+            from . import ops
+            self._gate_stream = torch.cuda.Stream(device=self.params[0].device)
+            ops.set_grad_sink(self)
         self.reset()
 
     def _close(self, plist):
@@ -62,6 +76,8 @@ class GradBucketReducer:
             flat.zero_()
         self._pending = [len(pl) for _, pl in self.buckets]
         self._handles = []
+        self._gate = {}
+        self._seq = 0
 
     def _on_grad_ready(self, p):
         b = self._owner[p]
@@ -69,9 +85,53 @@ class GradBucketReducer:
         if self._pending[b] == 0 and self.world > 1:
             self._handles.append(self._launch(b))
 
-    def _launch(self, b):
+    def _launch(self, b, gate=None):
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
-        return dist.all_reduce(self.buckets[b][0], op=op, group=self.group, async_op=True)
+        if gate is None:
+            return dist.all_reduce(self.buckets[b][0], op=op, group=self.group, async_op=True)
+        # the collective waits for whatever the *current* stream has queued: a stream that has queued nothing but the wait for
+        # the stage's event lets it start as soon as the bucket's gradients are final
+        self._gate_stream.wait_event(gate)
+        with torch.cuda.stream(self._gate_stream):
+            return dist.all_reduce(self.buckets[b][0], op=op, group=self.group, async_op=True)
+
+    # ---- gradient sink interface (functional.TrunkFunction.backward)
+    def grad_ptr(self, p):
+        """Device address of the bucket slice that is ``p.grad`` (None if the parameter is not ours or its .grad was replaced).
+        ``direct = False`` switches the sink off: a step that sends more than one backward pass through the same parameters
+        (Stage 2: the student runs on two batches) must let autograd sum the passes before a bucket is reduced."""
+        if not self.direct:
+            return None
+        b = self._owner.get(p)
+        if b is None or p.grad is None:
+            return None
+        flat = self.buckets[b][0]
+        ptr = p.grad.data_ptr()
+        if not (flat.data_ptr() <= ptr < flat.data_ptr() + flat.numel() * 4) or not p.grad.is_contiguous():
+            return None
+        return ptr
+
+    def stage_event(self, i: int):
+        ev = self._stage_events.get(i)
+        if ev is None:
+            ev = self._stage_events[i] = torch.cuda.Event()
+            ev.record()              # torch creates the CUDA event lazily, at the first record: the library needs the handle
+        return ev
+
+    def mark_ready(self, params, event):
+        """The gradients of ``params`` are complete once ``event`` has happened (they were accumulated into the buckets by the
+        kernels themselves; autograd sees no gradient for them and fires no hook)."""
+        self._seq += 1
+        touched = set()
+        for p in params:
+            b = self._owner[p]
+            self._pending[b] -= 1
+            self._gate[b] = (self._seq, event)
+            touched.add(b)
+        if self.world > 1:
+            for b in sorted(touched):
+                if self._pending[b] == 0:
+                    self._handles.append(self._launch(b, gate=self._gate[b][1]))
 
     def broadcast_buffers(self, module):
         """Rank 0's buffers (BN running statistics) to every rank; call once after construction."""

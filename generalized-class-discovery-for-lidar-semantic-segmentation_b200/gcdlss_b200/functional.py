@@ -657,7 +657,7 @@ class TrunkFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
-        from ._cabi import OP_ADD_COLS, OP_BLOCK_BACKWARD, Op
+        from ._cabi import OP_ADD_COLS, OP_BLOCK_BACKWARD, OP_RECORD_EVENT, Op
         plan, blocks_c, sizes, n_lv = ctx.plan, ctx.blocks_c, ctx.sizes, ctx.n_lv
         xd, act = ctx.keep[0], ctx.keep[1]
         dev, dt = xd.device, xd.dtype
@@ -670,10 +670,21 @@ class TrunkFunction(torch.autograd.Function):
             nb = _al(b.u1.n_out * b.u1.c_out * esz)
             gbytes += (3 if b.has_u2 else 1) * nb + (2 if b.has_ud else 1) * _al(b.u1.n_in * b.u1.c_in * esz)
         garena = _Bump(gbytes, dev)
-        grads = ops.zeros_f32.take(plan.sum_w + 2 * plan.sum_c, dev)
+        # Parameter gradients.  Default: a zero arena whose slices are handed to autograd.  With a gradient sink (a data-parallel
+        # reducer, ddp.GradBucketReducer) the kernels accumulate straight into the reducer's flat all-reduce buckets (zeroed by
+        # its reset()), nothing is returned to autograd for those parameters, and the reducer is told per network stage -- with
+        # an event the library records behind the stage's kernels -- which gradients are final, so the all-reduce of a bucket
+        # starts while the rest of the backward pass is still running.
+        sink = ops.grad_sink() if dev.type == "cuda" else None
+        sink_ptrs = None
+        if sink is not None:
+            sink_ptrs = [sink.grad_ptr(p) for p in plan.parameters()]
+            if any(q is None for q in sink_ptrs):
+                sink, sink_ptrs = None, None
+        grads = ops.zeros_f32.take(plan.sum_w + 2 * plan.sum_c, dev) if sink is None else None
         sums = ops.zeros_f64.take(2 * plan.sum_c, dev)
-        gp, sp = grads.data_ptr(), sums.data_ptr()
-        prog = (Op * (plan.n_blocks + 16))()
+        gp, sp = (grads.data_ptr() if grads is not None else 0), sums.data_ptr()
+        prog = (Op * (plan.n_blocks + 32))()
         n_ops = 0
         # parameter-gradient slots, in plan.units order (weights first, then [dgamma | dbeta] of the unit)
         unit_slots, woff, coff = [], 0, 0
@@ -709,6 +720,7 @@ class TrunkFunction(torch.autograd.Function):
             return g.data_ptr()
 
         keep = []
+        stage_done = []                        # (event, unit indices) per stage, in the order the stages finish
         # block index ranges per stage (forward order): encoder stage i = [single, blocks...], decoder likewise
         stages, bi = [], 0
         for conv, bn, blks in plan.encoder + plan.decoder:
@@ -754,7 +766,10 @@ class TrunkFunction(torch.autograd.Function):
                 for u, k in zip((b.u1, b.u2, b.ud), block_units[j]):
                     wo, size, go, c, co = unit_slots[k]
                     u.sums = sp + 16 * co
-                    u.dw, u.dgamma, u.dbeta = gp + 4 * wo, gp + 4 * go, gp + 4 * (go + c)
+                    if sink_ptrs is not None:
+                        u.dw, u.dgamma, u.dbeta = sink_ptrs[3 * k], sink_ptrs[3 * k + 1], sink_ptrs[3 * k + 2]
+                    else:
+                        u.dw, u.dgamma, u.dbeta = gp + 4 * wo, gp + 4 * go, gp + 4 * (go + c)
                 prog[n_ops].op, prog[n_ops].block = OP_BLOCK_BACKWARD, C.pointer(b)
                 n_ops += 1
                 if j > first:
@@ -772,8 +787,13 @@ class TrunkFunction(torch.autograd.Function):
                     c_up = blocks_c[first].u1.c_out
                     g_in[first], ld_in[first] = b.dx, c_i                      # left columns, strided
                     skip_extra[7 - s - 1] = (b.dx + c_up * esz, c_i)           # right columns -> the encoder stage of that resolution
+            if sink is not None:
+                ev = sink.stage_event(7 - s)
+                o = prog[n_ops]
+                o.op, o.dst = OP_RECORD_EVENT, ev.cuda_event
+                n_ops += 1
+                stage_done.append((ev, [k for j in range(first, last) for k in block_units[j]]))
         # the skip of tensor stride 1 is the trunk's input (the stem activation): its decoder slice joins dx of the first block
-        launches = C.c_int32(0)
         if need_dx and -1 in skip_extra:
             ptr, ld_src = skip_extra[-1]
             add_cols(blocks_c[0].dx, 0 or blocks_c[0].u1.c_in, ptr, ld_src, blocks_c[0].u1.n_in, blocks_c[0].u1.c_in)
@@ -785,6 +805,11 @@ class TrunkFunction(torch.autograd.Function):
             if dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)
         out = [None, None, dx]
+        if sink is not None:
+            params = plan.parameters()
+            for ev, units in stage_done:
+                sink.mark_ready([params[3 * k + i] for k in units for i in range(3)], ev)
+            return tuple(out + [None] * (3 * len(plan.units)))
         for (wo, size, go, c, _), (conv, _) in zip(unit_slots, plan.units):
             out += [grads[wo:wo + size].view(conv.kernel.shape), grads[go:go + c], grads[go + c:go + 2 * c]]
         return tuple(out)

@@ -95,6 +95,20 @@ class _ExecContexts:
 
 exec_contexts = _ExecContexts()
 
+# Gradient sink: a data-parallel reducer (ddp.GradBucketReducer) registers itself here; the trunk's backward pass then lets
+# the kernels accumulate parameter gradients straight into the reducer's buckets (functional.TrunkFunction.backward).
+_grad_sink = {"ref": None}
+
+
+def set_grad_sink(sink) -> None:
+    import weakref
+    _grad_sink["ref"] = weakref.ref(sink) if sink is not None else None
+
+
+def grad_sink():
+    r = _grad_sink["ref"]
+    return r() if r is not None else None
+
 
 def run_ops(prog, n_ops: int, backward: bool) -> int:
     """gcd_run_ops_exec on the current stream with that stream's execution context; returns the number of kernels launched."""

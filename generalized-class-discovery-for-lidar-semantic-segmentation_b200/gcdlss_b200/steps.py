@@ -172,6 +172,8 @@ class Stage2Harness:
         self.student, self.teacher, self.opt = student, teacher, optimizer
         self.voxel_size, self.mse_coeff, self.ema_momentum, self.num_areas = voxel_size, mse_coeff, ema_momentum, num_areas
         self.reducer = reducer
+        if reducer is not None:
+            reducer.direct = False       # two student passes per step accumulate into the same parameters (see GradBucketReducer.grad_ptr)
         self.fused_loss = fused_loss      # consistency terms through gcd_consistency_rows (one pass) instead of torch ops
         self._step = 0
         for p in self.teacher.parameters():

@@ -395,8 +395,11 @@ int32_t gcd_block_backward(gcd_block_args* args, void* stream);
  *   GCD_OP_BLOCK_FORWARD / _BACKWARD : gcd_block_forward / gcd_block_backward on `block`
  *   GCD_OP_COPY_COLS : dst[i, 0:c] = src[i, 0:c]  for i < n   (row pitches ld_dst / ld_src, elements of `dtype`)
  *   GCD_OP_ADD_COLS  : dst[i, 0:c] += src[i, 0:c]
+ *   GCD_OP_RECORD_EVENT : dst is a cudaEvent_t; it is recorded behind everything the call has issued so far on the caller's
+ *                      stream and on the context's side stream (a data-parallel caller starts the all-reduce of the parameter
+ *                      gradients a network stage has finished while the rest of the backward pass runs)
  * c, both pitches and both pointers must be multiples of 16 bytes.  *launches (host, optional) receives the kernel count. */
-typedef enum { GCD_OP_BLOCK_FORWARD = 0, GCD_OP_BLOCK_BACKWARD = 1, GCD_OP_COPY_COLS = 2, GCD_OP_ADD_COLS = 3 } gcd_op_kind;
+typedef enum { GCD_OP_BLOCK_FORWARD = 0, GCD_OP_BLOCK_BACKWARD = 1, GCD_OP_COPY_COLS = 2, GCD_OP_ADD_COLS = 3, GCD_OP_RECORD_EVENT = 4 } gcd_op_kind;
 typedef struct {
   int32_t op;                /* gcd_op_kind */
   int32_t dtype;             /* gcd_dtype (copy / add) */

@@ -434,16 +434,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    max_ahead = int(os.environ.get("GCDLSS_BENCH_MAX_AHEAD", "2"))
+    host_t = []
+
     def timed(fn, steps, finish=None):
         """(total ms, per-step device intervals in ms): K steps between two CUDA events after a barrier + synchronize on both
         sides (max over ranks), plus one event after every step for the step-time percentiles."""
         barrier()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         e1 = torch.cuda.Event(enable_timing=True)
+        host_t.clear()
         marks[0].record()
         for i in range(steps):
+            # The host stays at most `max_ahead` steps ahead of the GPU, as a training loop that reads its loss does (the e2e
+            # loop reads it one step late).  Unthrottled the host (6.9 ms of launch work per 9.6 ms step) runs further ahead
+            # every step until a driver queue fills, and the wait that follows showed up as single steps of 20-180 ms in
+            # about half of the runs (r2 calls 10-13, with and without the clock sampler).
+            if max_ahead > 0 and i >= max_ahead:
+                marks[i - max_ahead + 1].synchronize()
+            host_t.append(time.perf_counter())
             fn(i)
             marks[i + 1].record()
+        host_t.append(time.perf_counter())
         if finish is not None:
             finish()
         e1.record()
@@ -522,6 +534,7 @@ def run_ours(args):
     if reducer is not None:
         reducer.measure = True
     total_ms, step_ms = timed(step_resident, args.steps)
+    host_step_ms = [1e3 * (b - a) for a, b in zip(host_t, host_t[1:])]
     launches = ops.launch_counter["calls"] - launches0
     comm_exposed_ms = None
     if reducer is not None:                # time the training stream spent waiting for the gradient all-reduce (per step)
@@ -620,6 +633,7 @@ def run_ours(args):
 
     if os.environ.get("GCDLSS_BENCH_DUMP_STEPS") and rank == 0:
         print("step_ms resident:", " ".join(f"{v:.2f}" for v in step_ms), file=sys.stderr)
+        print("host_ms resident:", " ".join(f"{v:.2f}" for v in host_step_ms), file=sys.stderr)
         print("step_ms e2e:     ", " ".join(f"{v:.2f}" for v in e2e_step_ms), file=sys.stderr)
 
     descr = {"stage1": ("MinkUNet34RC backbone + final head (Stage-1 MinkUNetBase, ref modules/exp.py:249-267)",
@@ -636,6 +650,7 @@ def run_ours(args):
                            "voxels_per_s": voxels * world * args.steps / (total_ms / 1e3), "conv_gflop_per_step_per_gpu": total_gflop,
                            "model": descr[0], "classes": n_classes, "step": descr[1], "parallelism": f"dp{world}",
                            "l2": f"{n_batches} distinct batches rotate; per-step activations + maps exceed the 126 MB L2",
+                           "host_max_steps_ahead": max_ahead,
                            **path_cfg},
                 "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + 8 * scans_per_gpu,
                         "ms_per_step": e2e_ms / args.steps, "step_ms": pct(e2e_step_ms)},

@@ -14,7 +14,7 @@ int32_t bn_forward_train(const void* x, int64_t ld_x, int64_t n, int32_t c, doub
                          int64_t ld_res, int32_t relu, void* y, int64_t ld_y, int32_t dtype, void* stream);
 int32_t bn_backward_train(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y, int64_t n, int32_t c,
                           const float* mean, const float* invstd, const float* gamma, double* sums, int32_t relu, void* dx, int64_t ld_dx,
-                          void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream);
+                          void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream, const float* beta_mask);
 namespace {
 
 template <typename T>
@@ -192,8 +192,9 @@ int32_t unit_bn_bwd(const gcd_convbn* u, const void* dy, int64_t ld_dy, const vo
                     int32_t dtype, void* stream) {
   const int64_t ld = u->c_out;
   if (ld_dy == 0) ld_dy = ld;
+  // conv -> BN -> ReLU without a residual (dres == NULL): the mask can be re-derived from x, see bn_backward_train
   return bn_backward_train(dy, ld_dy, x, ld, y, y ? ld : 0, u->n_out, u->c_out, u->mean, u->invstd, u->gamma, u->sums, relu, dx, ld,
-                           dres, dres ? ld : 0, u->dgamma, u->dbeta, dtype, stream);
+                           dres, dres ? ld : 0, u->dgamma, u->dbeta, dtype, stream, (relu && !dres) ? u->beta : nullptr);
 }
 
 int32_t check_unit(const gcd_convbn* u, const char* who) {

@@ -11,6 +11,13 @@ namespace {
 constexpr int kRedX = 32, kRedY = 8;        // reduction kernels: 32 channel lanes x 8 row lanes
 constexpr int kMaxChanIter = 32;            // supports up to 1024 channels (MinkUNet50/101 bottlenecks at tensor stride 16: 256 x 4)
 constexpr int kMaxChannels = kRedX * kMaxChanIter;
+constexpr int kFusedBwdMaxChannels = 512;      // two-phase backward kernel: six per-channel arrays in shared memory next to the reduction scratch
+
+// Folded scale / shift of a training-mode batch norm, with explicit roundings: the backward pass of conv -> BN -> ReLU units
+// re-derives the ReLU mask from x as (x * scale + shift > 0) instead of reading the stored activation, which is only the
+// mask the forward pass applied if both sides compute scale and shift to the same bits.
+__device__ __forceinline__ float bn_scale_of(float g, float is) { return __fmul_rn(g, is); }
+__device__ __forceinline__ float bn_shift_of(float b, float m, float g, float is) { return __fmaf_rn(-__fmul_rn(m, g), is, b); }
 
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
@@ -139,8 +146,8 @@ __global__ void __launch_bounds__(kVecThreads) bn_apply_vec_kernel(const T* __re
       if (var < 0.0) var = 0.0;
       const float is = rsqrtf((float)var + eps);
       const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-      s_scale[ch] = g * is;
-      s_shift[ch] = b - (float)m * g * is;
+      s_scale[ch] = bn_scale_of(g, is);
+      s_shift[ch] = bn_shift_of(b, (float)m, g, is);
       if (blockIdx.x == 0) {
         mean_out[ch] = (float)m;
         invstd_out[ch] = is;
@@ -369,8 +376,8 @@ __device__ __forceinline__ void bn_apply_wide_body(const T* __restrict__ x, int6
       if (var < 0.0) var = 0.0;
       const float is = rsqrtf((float)var + eps);
       const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-      s_scale[ch] = g * is;
-      s_shift[ch] = b - (float)m * g * is;
+      s_scale[ch] = bn_scale_of(g, is);
+      s_shift[ch] = bn_shift_of(b, (float)m, g, is);
       if (blockIdx.x == 0) {
         mean_out[ch] = (float)m;
         invstd_out[ch] = is;
@@ -437,20 +444,25 @@ __global__ void __launch_bounds__(kVecThreads) bn_apply_wide_kernel(const T* __r
                                 res, ld_res, relu, y, ld_y, rows_per_block);
 }
 
-template <typename T, bool kCoherent = false>
+// kMaskFromX (two-phase kernel, ReLU without residual): the mask is (x * scale + shift > 0) re-derived from x (beta_mask != NULL)
+// and y is not read at all; kMaxC bounds the channel count (size of the per-channel arrays).
+template <typename T, bool kCoherent = false, int kMaxC = kMaxChannels, bool kMaskFromX = false>
 __device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x, int64_t ld_x,
                                                        const T* __restrict__ y, int64_t ld_y, int64_t n, int c,
                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                                        const float* __restrict__ gamma, const double* sums, int relu,
                                                        int training, T* __restrict__ dx, int64_t ld_dx, T* __restrict__ dres,
-                                                       int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block) {
+                                                       int64_t ld_dres, float* dgamma, float* dbeta, int rows_per_block,
+                                                       const float* __restrict__ beta_mask = nullptr) {
   constexpr int V = VecW<T>::V;
-  __shared__ float s_k[kMaxChannels], s_mean[kMaxChannels], s_is[kMaxChannels], s_sg[kMaxChannels], s_sgx[kMaxChannels];
+  __shared__ float s_k[kMaxC], s_mean[kMaxC], s_is[kMaxC], s_sg[kMaxC], s_sgx[kMaxC];
+  __shared__ float s_shift[kMaskFromX ? kMaxC : 1];
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   for (int ch = threadIdx.x; ch < c; ch += kVecThreads) {
     const float is = invstd[ch];
     const double sum_g = kCoherent ? __ldcg(&sums[ch]) : sums[ch], sum_gx = kCoherent ? __ldcg(&sums[c + ch]) : sums[c + ch];
-    s_k[ch] = (gamma ? gamma[ch] : 1.f) * is;
+    s_k[ch] = bn_scale_of(gamma ? gamma[ch] : 1.f, is);
+    if (kMaskFromX) s_shift[ch] = bn_shift_of(beta_mask[ch], mean[ch], gamma ? gamma[ch] : 1.f, is);
     s_mean[ch] = mean[ch];
     s_is[ch] = is;
     s_sg[ch] = training ? (float)sum_g * inv_n : 0.f;
@@ -473,11 +485,18 @@ __device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy,
     float ga[V], gb[V], xa[V], xb[V], ya[V], yb[V], o[V];
     VecW<T>::load(dy + a.r * ld_dy + a.g * V, ga);
     VecW<T>::load(x + a.r * ld_x + a.g * V, xa);
-    if (relu) VecW<T>::load(y + a.r * ld_y + a.g * V, ya);
+    if (relu && !kMaskFromX) VecW<T>::load(y + a.r * ld_y + a.g * V, ya);
     if (two) {
       VecW<T>::load(dy + b.r * ld_dy + b.g * V, gb);
       VecW<T>::load(x + b.r * ld_x + b.g * V, xb);
-      if (relu) VecW<T>::load(y + b.r * ld_y + b.g * V, yb);
+      if (relu && !kMaskFromX) VecW<T>::load(y + b.r * ld_y + b.g * V, yb);
+    }
+    if (kMaskFromX) {           // what the forward pass stored: relu(x * scale + shift)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        ya[j] = fmaf(xa[j], s_k[a.g * V + j], s_shift[a.g * V + j]);
+        if (two) yb[j] = fmaf(xb[j], s_k[b.g * V + j], s_shift[b.g * V + j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -546,8 +565,11 @@ struct BnBwdFusedArgs {
   const void* dy; int64_t ld_dy; const void* x; int64_t ld_x; const void* y; int64_t ld_y; int64_t n; int c;
   const float* mean; const float* invstd; const float* gamma; double* sums; int relu;
   void* dx; int64_t ld_dx; void* dres; int64_t ld_dres; float* dgamma; float* dbeta; int rows_per_block;
+  const float* beta;      // kMaskFromX kernels: the forward pass's beta (mask = x * scale + shift > 0)
 };
-template <typename T>
+// kMaskFromX: conv -> BN -> ReLU units (no residual): both phases read dy and x only; the activation (one of three operand
+// streams of the reduction, one of three reads of the elementwise phase) stays in HBM.
+template <typename T, bool kMaskFromX>
 __global__ void __launch_bounds__(kVecThreads, 3) bn_bwd_fused_wide_kernel(const BnBwdFusedArgs a) {
   pdl_trigger(); pdl_wait();
   constexpr int V = VecW<T>::V;
@@ -555,16 +577,28 @@ __global__ void __launch_bounds__(kVecThreads, 3) bn_bwd_fused_wide_kernel(const
   const T* x = static_cast<const T*>(a.x);
   const T* y = static_cast<const T*>(a.y);
   {
-    __shared__ float s_mean[kMaxChannels], s_is[kMaxChannels];
+    __shared__ float s_mean[kFusedBwdMaxChannels], s_is[kFusedBwdMaxChannels];
     for (int ch = threadIdx.x; ch < a.c; ch += kVecThreads) { s_mean[ch] = a.mean[ch]; s_is[ch] = a.invstd[ch]; }
     __syncthreads();
+    // a thread of the reduction owns one group of V channels for all its rows: its folded scale / shift live in registers
+    float sc[V], sh[V];
+    if (kMaskFromX) {
+      const int ch0 = (int)(threadIdx.x % (a.c / V)) * V;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float g = a.gamma ? a.gamma[ch0 + j] : 1.f;
+        sc[j] = bn_scale_of(g, s_is[ch0 + j]);
+        sh[j] = bn_shift_of(a.beta[ch0 + j], s_mean[ch0 + j], g, s_is[ch0 + j]);
+      }
+    }
     column_reduce2_wide<T, V, 2>(a.n, a.c, a.rows_per_block, a.sums, [&](int64_t r, int ch, float (&va)[V], float (&vb)[V]) {
       float xv[V], yv[V];
       VecW<T>::load(dy + r * a.ld_dy + ch, va);
       VecW<T>::load(x + r * a.ld_x + ch, xv);
-      if (a.relu) VecW<T>::load(y + r * a.ld_y + ch, yv);
+      if (a.relu && !kMaskFromX) VecW<T>::load(y + r * a.ld_y + ch, yv);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
+        if (kMaskFromX) yv[j] = fmaf(xv[j], sc[j], sh[j]);
         if (a.relu && !(yv[j] > 0.f)) va[j] = 0.f;
         vb[j] = va[j] * (xv[j] - s_mean[ch + j]) * s_is[ch + j];
       }
@@ -572,8 +606,9 @@ __global__ void __launch_bounds__(kVecThreads, 3) bn_bwd_fused_wide_kernel(const
   }
   __threadfence();
   cooperative_groups::this_grid().sync();
-  bn_bwd_apply_wide_body<T, true>(dy, a.ld_dy, x, a.ld_x, y, a.ld_y, a.n, a.c, a.mean, a.invstd, a.gamma, a.sums, a.relu, 1, static_cast<T*>(a.dx),
-                                  a.ld_dx, static_cast<T*>(a.dres), a.ld_dres, a.dgamma, a.dbeta, a.rows_per_block);
+  bn_bwd_apply_wide_body<T, true, kFusedBwdMaxChannels, kMaskFromX>(dy, a.ld_dy, x, a.ld_x, y, a.ld_y, a.n, a.c, a.mean, a.invstd, a.gamma, a.sums,
+                                                                    a.relu, 1, static_cast<T*>(a.dx), a.ld_dx, static_cast<T*>(a.dres), a.ld_dres,
+                                                                    a.dgamma, a.dbeta, a.rows_per_block, a.beta);
 }
 
 template <typename T>
@@ -857,7 +892,10 @@ template <typename Kernel> int coop_blocks_per_sm(Kernel k) {
   return b;
 }
 template <typename T> int fwd_fused_occupancy() { static const int v = coop_blocks_per_sm(bn_fwd_fused_wide_kernel<T>); return v; }
-template <typename T> int bwd_fused_occupancy() { static const int v = coop_blocks_per_sm(bn_bwd_fused_wide_kernel<T>); return v; }
+template <typename T> int bwd_fused_occupancy() {
+  static const int v = std::min(coop_blocks_per_sm(bn_bwd_fused_wide_kernel<T, false>), coop_blocks_per_sm(bn_bwd_fused_wide_kernel<T, true>));
+  return v;
+}
 // rows per block of a cooperative launch: the partition of the stand-alone reduction when it fits on the GPU at once, fatter
 // blocks otherwise
 template <typename T> int coop_rows(int64_t n, int c, int occupancy) {
@@ -895,20 +933,25 @@ int32_t bn_forward_train(const void* x, int64_t ld_x, int64_t n, int32_t c, doub
 }
 
 // the same for the backward pass (training mode): sums [2c] zero on entry
+// beta_mask (optional): the unit is conv -> BN -> ReLU without a residual and its forward pass ran through bn_forward_train of
+// this library: the two-phase kernel re-derives the ReLU mask from x and does not read y (GCD_OPT_BN_MASK_FROM_X).
 int32_t bn_backward_train(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, const void* y, int64_t ld_y, int64_t n, int32_t c,
                           const float* mean, const float* invstd, const float* gamma, double* sums, int32_t relu, void* dx, int64_t ld_dx,
-                          void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream) {
-  if (n > 0 && option(GCD_OPT_BN_FUSED)) {
-    BnBwdFusedArgs a{dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, dx, ld_dx, dres, ld_dres, dgamma, dbeta, 0};
+                          void* dres, int64_t ld_dres, float* dgamma, float* dbeta, int32_t dtype, void* stream, const float* beta_mask) {
+  if (n > 0 && option(GCD_OPT_BN_FUSED) && c <= kFusedBwdMaxChannels) {
+    const bool from_x = relu && beta_mask != nullptr && dres == nullptr && option(GCD_OPT_BN_MASK_FROM_X);
+    BnBwdFusedArgs a{dy, ld_dy, x, ld_x, y, ld_y, n, c, mean, invstd, gamma, sums, relu, dx, ld_dx, dres, ld_dres, dgamma, dbeta, 0, beta_mask};
     cudaError_t e = cudaErrorInvalidValue;
     if (dtype == GCD_BF16 && wide_ok<__nv_bfloat16>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}) &&
         bwd_fused_occupancy<__nv_bfloat16>() > 0) {
       a.rows_per_block = bwd_partition_rows<__nv_bfloat16>(n, c);
-      e = launch_coop_pdl(bn_bwd_fused_wide_kernel<__nv_bfloat16>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
+      e = launch_coop_pdl(from_x ? bn_bwd_fused_wide_kernel<__nv_bfloat16, true> : bn_bwd_fused_wide_kernel<__nv_bfloat16, false>,
+                          dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
     } else if (dtype == GCD_F32 && wide_ok<float>(c, {ld_dy, ld_x, relu ? ld_y : 0, ld_dx, dres ? ld_dres : 0}, {dy, x, relu ? y : nullptr, dx, dres}) &&
                bwd_fused_occupancy<float>() > 0) {
       a.rows_per_block = bwd_partition_rows<float>(n, c);
-      e = launch_coop_pdl(bn_bwd_fused_wide_kernel<float>, dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
+      e = launch_coop_pdl(from_x ? bn_bwd_fused_wide_kernel<float, true> : bn_bwd_fused_wide_kernel<float, false>,
+                          dim3(rows_grid(n, a.rows_per_block)), dim3(kVecThreads), as_stream(stream), a);
     }
     if (e == cudaSuccess) return GCD_OK;
     cudaGetLastError();

@@ -127,4 +127,9 @@ int32_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* 
 int32_t pairs_from_table_fused(const int32_t* nbr, int64_t n_out, int kv, int32_t* pair_in, int32_t* pair_out, int32_t* pair_off,
                                int32_t* total_pairs, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// the same lists in ONE pass over the table (decoupled look-back, scan.cu); workspace >= pairs_lookback_workspace_bytes(n_out * kv)
+size_t pairs_lookback_workspace_bytes(int64_t total_entries);
+int32_t pairs_from_table_lookback(const int32_t* nbr, int64_t n_out, int kv, int32_t* pair_in, int32_t* pair_out, int32_t* pair_off,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace gcd

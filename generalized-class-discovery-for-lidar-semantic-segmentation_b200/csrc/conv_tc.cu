@@ -303,13 +303,15 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
       const int64_t tm = pos / p.n_tiles_n;
       return (p.dyn_ascending ? tm : tiles_m - 1 - tm) * p.n_tiles_n + pos % p.n_tiles_n;
     };
-    auto claim = [&]() -> int64_t {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(p.sched, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      return tile_at((int64_t)gridDim.x + t);
-    };
+    // The atomic of the tile after next is issued one iteration before its result is looked at: its round trip (and then the
+    // mask load that depends on it) overlaps the staging of a whole tile instead of standing in front of every tile.
+    int raw_ticket = 0;
+    bool have_ticket = false;
     int64_t next_work = dyn ? tile_at(blockIdx.x) : static_work(0);
+    if (dyn && next_work >= 0) {
+      if (lane == 0) raw_ticket = atomicAdd(p.sched, 1);
+      have_ticket = true;
+    }
     if (compact && next_work >= 0) next_mask = __ldg(&p.tile_masks[next_work / p.n_tiles_n]);
     const uint32_t max_ahead = dyn ? (uint32_t)p.dyn_ahead : (uint32_t)kTableSlots;
 #ifdef GCD_TC_PROFILE
@@ -334,7 +336,16 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
       }
       const int64_t row0 = (work / p.n_tiles_n) * kTileM;
       uint32_t mask = next_mask;
-      next_work = dyn ? claim() : static_work(tile_seq + 1);
+      if (dyn) {
+        next_work = have_ticket ? tile_at((int64_t)gridDim.x + __shfl_sync(0xffffffffu, raw_ticket, 0)) : -1;
+        have_ticket = false;
+        if (next_work >= 0) {
+          if (lane == 0) raw_ticket = atomicAdd(p.sched, 1);
+          have_ticket = true;
+        }
+      } else {
+        next_work = static_work(tile_seq + 1);
+      }
       if (compact && next_work >= 0) next_mask = __ldg(&p.tile_masks[next_work / p.n_tiles_n]);   // one tile ahead
       const uint32_t load_mask = mask ? mask : 1u;         // degenerate tile: offset 0 runs with all-zero rows
       const uint32_t n_sl = compact ? (uint32_t)__popc(load_mask) : (uint32_t)p.kv;

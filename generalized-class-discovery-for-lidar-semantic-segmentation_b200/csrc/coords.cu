@@ -489,7 +489,11 @@ extern "C" int32_t gcd_kmap_up2(const int32_t* parent, const int32_t* code, int6
 }
 
 extern "C" size_t gcd_pairs_workspace_bytes(int64_t n_out, int32_t kv) {
+  // sized for the form GCD_OPT_PAIRS_FUSED selects at the time of the query (the call checks against the form it runs)
   int64_t total = (n_out > 0 ? n_out : 1) * (int64_t)kv;
+  const int form = option(GCD_OPT_PAIRS_FUSED);
+  if (form == 2) return pairs_lookback_workspace_bytes(total);
+  if (form == 1) return align_up(4, 256) + scan_workspace_bytes(total);
   return align_up((size_t)total * 4, 256) * 2 + align_up(4, 256) + scan_workspace_bytes(total);
 }
 extern "C" int32_t gcd_pairs_from_table(const int32_t* nbr, int64_t n_out, int32_t kv, int32_t* pair_in, int32_t* pair_out,
@@ -500,10 +504,15 @@ extern "C" int32_t gcd_pairs_from_table(const int32_t* nbr, int64_t n_out, int32
   if (n_out == 0) { cudaMemsetAsync(pair_off, 0, (size_t)(kv + 1) * 4, st); return GCD_OK; }
   const int64_t total = n_out * kv;
   char* p = static_cast<char*>(workspace);
+  const int form = option(GCD_OPT_PAIRS_FUSED);
+  if (form == 2) return pairs_from_table_lookback(nbr, n_out, kv, pair_in, pair_out, pair_off, workspace, workspace_bytes, st);
+  if (form == 1) {
+    int32_t* tot1 = (int32_t*)p;
+    return pairs_from_table_fused(nbr, n_out, kv, pair_in, pair_out, pair_off, tot1, p + align_up(4, 256), scan_workspace_bytes(total), st);
+  }
   int32_t* flags = (int32_t*)p; p += align_up((size_t)total * 4, 256);
   int32_t* pos = (int32_t*)p;   p += align_up((size_t)total * 4, 256);
   int32_t* tot = (int32_t*)p;   p += align_up(4, 256);
-  if (option(GCD_OPT_PAIRS_FUSED)) return pairs_from_table_fused(nbr, n_out, kv, pair_in, pair_out, pair_off, tot, p, scan_workspace_bytes(total), st);
   flag_valid_kernel<<<grid_for(total), kThreads, 0, st>>>(nbr, total, flags);
   int32_t rc = exclusive_scan_i32(flags, pos, total, tot, p, scan_workspace_bytes(total), st);
   if (rc != GCD_OK) return rc;

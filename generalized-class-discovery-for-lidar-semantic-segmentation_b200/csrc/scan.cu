@@ -125,7 +125,105 @@ __global__ void __launch_bounds__(kScanThreads) pairs_emit_fused_kernel(const in
     }
   }
 }
+// ---- single-pass pair-list build (GCD_PAIRS_FUSED=2): decoupled look-back.  One launch reads the table ONCE: a block takes a
+// tile of 4096 entries by ticket (tiles are started in order, so every predecessor of a running tile is running or done),
+// counts its valid entries, publishes the count, sums its predecessors' published counts backwards until it meets one that
+// already knows its inclusive prefix, publishes its own, and writes its pairs.  state[tile] = status << 32 | value with status
+// 0 = nothing yet, 1 = the tile's own count, 2 = inclusive prefix; state and ticket are zero on entry (one memset).
+constexpr int kLbItems = 16;
+constexpr int kLbTile = kScanThreads * kLbItems;   // 4096
+constexpr unsigned long long kLbAggregate = 1ull << 32, kLbInclusive = 2ull << 32;
+
+__global__ void __launch_bounds__(kScanThreads) pairs_lookback_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int kv,
+                                                                       unsigned long long* state, int32_t* ticket,
+                                                                       int32_t* __restrict__ pair_in, int32_t* __restrict__ pair_out,
+                                                                       int32_t* __restrict__ pair_off) {
+  __shared__ int s_tile, s_prefix;
+  const int64_t total_entries = n_out * kv;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t base = (int64_t)tile * kLbTile + (int64_t)threadIdx.x * kLbItems;
+  int v[kLbItems];
+  int sum = 0;
+  if (base + kLbItems <= total_entries && (reinterpret_cast<uintptr_t>(nbr) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < kLbItems; i += 4) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(nbr + base + i));
+      v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kLbItems; ++i) v[i] = (base + i < total_entries) ? __ldg(&nbr[base + i]) : -1;
+  }
+#pragma unroll
+  for (int i = 0; i < kLbItems; ++i) sum += v[i] >= 0 ? 1 : 0;
+  int total;
+  int pos = block_exclusive_scan(sum, &total);
+  if (threadIdx.x == 0) {
+    // tile 0 knows its inclusive prefix at once
+    atomicExch(&state[tile], (tile == 0 ? kLbInclusive : kLbAggregate) | (unsigned)total);
+    if (tile == 0) s_prefix = 0;
+  }
+  if (tile > 0 && threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int prefix = 0;
+    for (int look = tile - 1;; look -= 32) {
+      const int t = look - lane;                       // lane 0 looks at the nearest predecessor
+      unsigned long long st = kLbInclusive;            // tiles before the first: an inclusive prefix of 0
+      if (t >= 0) {
+        do { st = *reinterpret_cast<volatile unsigned long long*>(&state[t]); } while ((st >> 32) == 0);
+      }
+      const unsigned incl = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const int first = incl ? __ffs(incl) - 1 : 32;   // nearest predecessor with an inclusive prefix
+      int val = lane <= first ? (int)(unsigned)st : 0; // aggregates of the nearer ones + that inclusive prefix
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+      prefix += val;
+      if (incl) break;
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&state[tile], kLbInclusive | (unsigned)(prefix + total));
+      s_prefix = prefix;
+    }
+  }
+  __syncthreads();
+  pos += s_prefix;
+  // entry t = k * n_out + o: the offset k of this thread's first entry by one division, then by counting
+  int64_t k = base < total_entries ? base / n_out : 0, o = base - k * n_out;
+#pragma unroll
+  for (int i = 0; i < kLbItems; ++i) {
+    if (base + i < total_entries) {
+      if (o == 0) pair_off[k] = pos;                   // first entry of offset k: where its list starts
+      if (v[i] >= 0) { pair_in[pos] = v[i]; pair_out[pos] = (int32_t)o; ++pos; }
+      if (base + i == total_entries - 1) pair_off[kv] = pos;
+      if (++o == n_out) { o = 0; ++k; }
+    }
+  }
+}
 }  // namespace
+
+size_t pairs_lookback_workspace_bytes(int64_t total_entries) {
+  return align_up((size_t)(ceil_div(total_entries > 0 ? total_entries : 1, kLbTile)) * 8 + 8, 256);
+}
+
+int32_t pairs_from_table_lookback(const int32_t* nbr, int64_t n_out, int kv, int32_t* pair_in, int32_t* pair_out, int32_t* pair_off,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int64_t total_entries = n_out * kv;
+  const size_t need = pairs_lookback_workspace_bytes(total_entries);
+  if (workspace_bytes < need) {
+    set_error("pairs_from_table_lookback: workspace too small");
+    return GCD_ERR_WORKSPACE;
+  }
+  const int64_t n_tiles = ceil_div(total_entries, kLbTile);
+  if (const cudaError_t e = cudaMemsetAsync(workspace, 0, need, stream); e != cudaSuccess) return cuda_fail(e, "gcd_pairs_from_table(memset)");
+  unsigned long long* state = static_cast<unsigned long long*>(workspace);
+  int32_t* ticket = reinterpret_cast<int32_t*>(state + n_tiles);
+  pairs_lookback_kernel<<<(unsigned)n_tiles, kScanThreads, 0, stream>>>(nbr, n_out, kv, state, ticket, pair_in, pair_out, pair_off);
+  GCD_LAUNCH_CHECK("gcd_pairs_from_table(look-back)");
+  return GCD_OK;
+}
 
 int32_t pairs_from_table_fused(const int32_t* nbr, int64_t n_out, int kv, int32_t* pair_in, int32_t* pair_out, int32_t* pair_off,
                                int32_t* total_pairs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {

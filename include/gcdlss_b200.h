@@ -78,7 +78,8 @@ int32_t gcd_has_tcgen05(void);
  * thread are safe, a call in flight sees either the old or the new value.  Initial values come from the environment
  * variable of the same name (GCD_PAIRS_FUSED, ...) read once, at the first use of the library, then never again. */
 typedef enum {
-  GCD_OPT_PAIRS_FUSED = 0,   /* 1 (default): pair lists straight from the table, two passes; 0: flag / scan / emit */
+  GCD_OPT_PAIRS_FUSED = 0,   /* gcd_pairs_from_table: 2 (default) one pass over the table (decoupled look-back); 1: two passes
+                                (count, scan of the tile counts, emit); 0: flag / scan / emit.  Identical lists. */
   GCD_OPT_GATHER_FLAT = 1,   /* 1 (default): gcd_rows_gather deals float4 elements flat; 0: one warp per row */
   GCD_OPT_TC_STAGES = 2,     /* > 0: cap on the shared-memory ring depth of the tcgen05 convolution (tuning aid) */
   GCD_OPT_TC_GROUP = 3,      /* 1 | 2 | 4 | 8: gather warps per ring slot; 0 = chosen per launch (tuning aid) */
@@ -98,7 +99,10 @@ typedef enum {
   GCD_OPT_DYN_TILES = 10,    /* gcd_run_ops_exec: 1: dynamic tile schedule of the tcgen05 kernels (heaviest tiles first); 2: the same in
                                 table order; 0 (default): static striding (measured faster on an otherwise idle GPU, r2 call 9) */
   GCD_OPT_DYN_AHEAD = 11,    /* > 0: tiles a CTA of the forward / dgrad kernel may claim ahead under the dynamic schedule (1..8, tuning aid) */
-  GCD_OPT_COUNT_ = 12
+  GCD_OPT_BN_MASK_FROM_X = 12, /* 1 (default): the fused batch-norm backward of conv -> BN -> ReLU units inside gcd_block_backward re-derives
+                                  the ReLU mask from the convolution output (x * scale + shift > 0, the forward pass's own arithmetic)
+                                  and does not read the stored activation; 0: reads it */
+  GCD_OPT_COUNT_ = 13
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);

@@ -62,6 +62,29 @@ def test_pair_lists(cuda):
         assert km.num_pairs() == off[-1]
 
 
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_pair_list_forms_agree(cuda, form):
+    """gcd_pairs_from_table as flag / scan / emit (0), two passes over the table (1) and one pass with decoupled look-back (2):
+    the same lists, on a table that spans many look-back tiles and on tables smaller than one."""
+    from gcdlss_b200 import _cabi, ops
+    from gcdlss_b200 import synth
+    prev = ops.get_option(_cabi.OPT_PAIRS_FUSED)
+    ops.set_option(_cabi.OPT_PAIRS_FUSED, form)
+    try:
+        clouds = [small_cloud(1, 1, spread=0.3, batch=0), small_cloud(2, 150, spread=0.3, batch=0),
+                  oq.batched_coordinates([oq.sparse_quantize_me(synth.make_scan("kitti", i, n_points=40000)[0], 0.05)[0] for i in range(2)])]
+        for bc in clouds:
+            for ks in (3, 5):
+                table = ocd.kmap_subm(bc, ks, 1)
+                pi, po, off = ocd.pairs_from_table(table)
+                gi, go, goff = ops.pairs_from_table(torch.from_numpy(np.ascontiguousarray(table.T)).cuda())
+                np.testing.assert_array_equal(goff.cpu().numpy(), off)
+                np.testing.assert_array_equal(gi.cpu().numpy()[: off[-1]], pi)
+                np.testing.assert_array_equal(go.cpu().numpy()[: off[-1]], po)
+    finally:
+        ops.set_option(_cabi.OPT_PAIRS_FUSED, prev)
+
+
 def test_lasermix_batch_ids_and_negative_coords(cuda):
     # batch ids 0,20,40,60 (ref exp_merge_mean_teacher.py:2856 quirk) and negative coordinates
     parts = [small_cloud(10 + i, 500, spread=0.5, batch=20 * i) for i in range(4)]

@@ -55,6 +55,13 @@ def _compare(a, b, mode):
         if k.startswith("d") and k.endswith("kernel"):        # fp32 atomics: order of accumulation differs run to run
             err = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-30))
             assert err < 1e-4, (k, err)
+        elif k != "out" and k != "dx" and ("norm" in k or ".bn." in k or k.startswith("dbn")):
+            # batch-norm parameter gradients are sums over rows: the C-sequenced path's two-phase kernel (for conv -> BN -> ReLU
+            # units the variant that re-derives the ReLU mask from x) and the stand-alone reduction are different kernels with
+            # their own fma contraction, so the fp32 sums may differ in the last bits.  (dx stays bit-identical in bf16: the
+            # masks are the same.)
+            err = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-30))
+            assert err < 2e-6, (k, err)
         elif mode == "fp32" and k != "out":
             # backward: the C-sequenced path runs the two-phase batch-norm kernel, the per-launch path the two stand-alone passes:
             # the same source, but ptxas decides mul/add -> fma contraction per kernel, so fp32 values may differ in the last

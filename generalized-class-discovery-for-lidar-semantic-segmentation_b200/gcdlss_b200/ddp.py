@@ -61,12 +61,15 @@ class GradBucketReducer:
         self.reset()
 
     def _close(self, plist):
-        n = sum(p.numel() for p in plist)
-        flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
-        off = 0
+        # every slice starts on a 16-byte boundary: the weight-gradient kernels that accumulate straight into the buckets
+        # (gradient sink) use 16-byte vector reductions; the padding is all-reduced along (zeros)
+        offs, n = [], 0
         for p in plist:
+            offs.append(n)
+            n += (p.numel() + 3) & ~3
+        flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
+        for p, off in zip(plist, offs):
             p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
             self._owner[p] = len(self.buckets)
         self.buckets.append((flat, list(plist)))
 
@@ -107,7 +110,7 @@ class GradBucketReducer:
             return None
         flat = self.buckets[b][0]
         ptr = p.grad.data_ptr()
-        if not (flat.data_ptr() <= ptr < flat.data_ptr() + flat.numel() * 4) or not p.grad.is_contiguous():
+        if not (flat.data_ptr() <= ptr < flat.data_ptr() + flat.numel() * 4) or not p.grad.is_contiguous() or ptr % 16:
             return None
         return ptr
 

@@ -249,6 +249,32 @@ __global__ void __launch_bounds__(256) im2col_kernel(const Tin* __restrict__ in,
   }
   out[t] = from_f32<Tout>(v);
 }
+// The same through a shared-memory transpose, for the shapes the stem uses (c_in == 1, ld_out <= 128): a block takes 32 output
+// rows; warp w reads the table entries of offsets k = w, w + 8, ... for those 32 rows (one 128-byte line per offset, where the
+// element-per-thread form above reads one line per *thread*), gathers the input value and parks it in a [32][ld_out] tile that
+// is then written row by row, coalesced.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) im2col_c1_kernel(const Tin* __restrict__ in, int64_t ld_in, const int32_t* __restrict__ nbr, int kv,
+                                                         int64_t n_out, Tout* __restrict__ out, int ld_out) {
+  pdl_trigger(); pdl_wait();
+  __shared__ float tile[32][129];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t o0 = (int64_t)blockIdx.x * 32;
+  const int64_t o = o0 + lane;
+  for (int k = warp; k < ld_out; k += 8) {
+    float v = 0.f;
+    if (k < kv && o < n_out) {
+      const int src = __ldg(&nbr[(int64_t)k * n_out + o]);
+      if (src >= 0) v = to_f32<Tin>(in[(int64_t)src * ld_in]);
+    }
+    tile[lane][k] = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * ld_out; idx += 256) {
+    const int r = idx / ld_out, c = idx - r * ld_out;
+    if (o0 + r < n_out) out[(o0 + r) * ld_out + c] = from_f32<Tout>(tile[r][c]);
+  }
+}
 }  // namespace
 
 int32_t conv_forward_simt(const gcd_conv_args* a, cudaStream_t st) {
@@ -302,6 +328,16 @@ extern "C" int32_t gcd_im2col(const void* in, int64_t ld_in, int32_t c_in, const
   GCD_REQUIRE(ld_out >= (int64_t)kv * c_in, "gcd_im2col: ld_out smaller than kv*c_in");
   if (n_out == 0) return GCD_OK;
   cudaStream_t st = as_stream(stream);
+  if (c_in == 1 && ld_out <= 128 && n_out > 0) {          // the 5x5x5 stem on a one-channel input
+    const dim3 grid((unsigned)ceil_div(n_out, 32)), block(256);
+    cudaError_t e;
+    if (in_dtype == GCD_F32 && out_dtype == GCD_F32) e = launch_pdl(im2col_c1_kernel<float, float>, grid, block, 0, st, (const float*)in, ld_in, nbr, kv, n_out, (float*)out, (int)ld_out);
+    else if (in_dtype == GCD_F32 && out_dtype == GCD_BF16) e = launch_pdl(im2col_c1_kernel<float, __nv_bfloat16>, grid, block, 0, st, (const float*)in, ld_in, nbr, kv, n_out, (__nv_bfloat16*)out, (int)ld_out);
+    else if (in_dtype == GCD_BF16 && out_dtype == GCD_BF16) e = launch_pdl(im2col_c1_kernel<__nv_bfloat16, __nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)in, ld_in, nbr, kv, n_out, (__nv_bfloat16*)out, (int)ld_out);
+    else e = launch_pdl(im2col_c1_kernel<__nv_bfloat16, float>, grid, block, 0, st, (const __nv_bfloat16*)in, ld_in, nbr, kv, n_out, (float*)out, (int)ld_out);
+    if (e != cudaSuccess) return cuda_fail(e, "gcd_im2col");
+    return GCD_OK;
+  }
   unsigned g = (unsigned)ceil_div(n_out * ld_out, 256);
   if (in_dtype == GCD_F32 && out_dtype == GCD_F32)
     im2col_kernel<float, float><<<g, 256, 0, st>>>((const float*)in, ld_in, c_in, nbr, kv, n_out, (float*)out, ld_out);

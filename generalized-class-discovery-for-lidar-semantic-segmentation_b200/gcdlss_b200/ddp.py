@@ -26,6 +26,7 @@ class GradBucketReducer:
                     dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
         # NCCL averages in the collective itself (ReduceOp.AVG): no separate divide pass over the 151 MB of gradients
         self._avg = self.world > 1 and dist.get_backend(process_group) == "nccl"
+        self.trace = None            # diagnostics (tools/ddp_check.py): a list collects (event, bucket, ...) tuples
         self.measure = False         # bench.py: CUDA events around the wait in finish() -> exposed communication time
         self.exposed_events = []
         self.buckets = []            # (flat tensor, [params])
@@ -50,7 +51,9 @@ class GradBucketReducer:
         # on a gate stream, i.e. while the rest of the backward pass is still running, instead of behind everything queued so far.
         import os
         self.direct = os.environ.get("GCDLSS_DDP_DIRECT", "1") not in ("0", "")      # A/B switch for the gradient sink
+        self.use_gate = os.environ.get("GCDLSS_DDP_GATE", "1") not in ("0", "")      # 0: buckets of the sink go out behind everything queued so far
         self._gate = {}              # bucket -> (sequence number, event) of the latest stage that touched it
+        self._sunk = set()           # parameters whose gradient arrived through the sink in the current step
         self._stage_events = {}
         self._seq = 0
         self._gate_stream = None
@@ -81,14 +84,21 @@ class GradBucketReducer:
         self._handles = []
         self._gate = {}
         self._seq = 0
+        self._sunk = set()
 
     def _on_grad_ready(self, p):
+        if p in self._sunk:          # autograd runs the (empty) accumulation of a parameter whose gradient went through the sink
+            return                   # and fires its post-accumulate hook all the same: that parameter was counted by mark_ready()
         b = self._owner[p]
+        if self.trace is not None:
+            self.trace.append(("hook", b, tuple(p.shape), torch.cuda.current_stream().cuda_stream))
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.world > 1:
             self._handles.append(self._launch(b))
 
     def _launch(self, b, gate=None):
+        if self.trace is not None:
+            self.trace.append(("launch", b, gate is not None, list(self._pending), torch.cuda.current_stream().cuda_stream))
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         if gate is None:
             return dist.all_reduce(self.buckets[b][0], op=op, group=self.group, async_op=True)
@@ -130,11 +140,12 @@ class GradBucketReducer:
             b = self._owner[p]
             self._pending[b] -= 1
             self._gate[b] = (self._seq, event)
+            self._sunk.add(p)
             touched.add(b)
         if self.world > 1:
             for b in sorted(touched):
                 if self._pending[b] == 0:
-                    self._handles.append(self._launch(b, gate=self._gate[b][1]))
+                    self._handles.append(self._launch(b, gate=self._gate[b][1] if self.use_gate else None))
 
     def broadcast_buffers(self, module):
         """Rank 0's buffers (BN running statistics) to every rank; call once after construction."""

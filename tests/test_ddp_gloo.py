@@ -67,3 +67,31 @@ def test_shard_scans_partition():
         assert sorted(allidx) == list(range(16))
     assert [len(shard_scans(10, r, 4)) for r in range(4)] == [3, 3, 2, 2]                      # no trailing scan is dropped
     assert sorted(sum((shard_scans(10, r, 4) for r in range(4)), [])) == list(range(10))
+
+
+def test_sink_bookkeeping_ignores_the_hooks_of_sunk_parameters():
+    """Gradient sink (functional.TrunkFunction.backward -> GradBucketReducer.mark_ready): autograd still runs the empty
+    accumulation of a parameter whose gradient went straight into the bucket and fires its post-accumulate hook; counting that
+    hook a second time used to send a bucket out before the parameters that really come later (the stem) had arrived
+    (found on two GPUs by tools/ddp_check.py).  Single process, the launches recorded instead of issued."""
+    from gcdlss_b200.ddp import GradBucketReducer
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (8, 8, 8, 8, 8, 8)]
+    red = GradBucketReducer(params, bucket_bytes=3 * 8 * 4)          # two buckets of three parameters, reverse order
+    assert [len(pl) for _, pl in red.buckets] == [3, 3]
+    launched = []
+    red.world = 2
+    red._launch = lambda b, gate=None: launched.append((b, gate)) or len(launched)
+    red.reset()
+    late, sunk = params[0], params[1:]                                # params[0] (registered first) gets its gradient last, by autograd
+    assert red.grad_ptr(sunk[0]) is None or red.grad_ptr(sunk[0]) % 16 == 0
+    red.mark_ready(sunk[2:], "event A")                               # bucket 0 = params 5, 4, 3: complete -> goes out behind event A
+    assert launched == [(0, "event A")]
+    red.mark_ready(sunk[:2], "event B")                               # bucket 1 = params 2, 1, 0: two of three
+    assert launched == [(0, "event A")]
+    for p in sunk:                                                    # autograd's hooks for the sunk parameters: no effect
+        red._on_grad_ready(p)
+    assert launched == [(0, "event A")] and red._pending == [0, 1]
+    red._on_grad_ready(late)                                          # the real late gradient completes bucket 1, ungated
+    assert launched == [(0, "event A"), (1, None)]
+    red.reset()
+    assert not red._sunk and red._pending == [3, 3]

@@ -42,16 +42,43 @@ def step(direct):
 
 
 g_hooks = step(False)
+reducer.trace = []
 g_sink = step(True)
+if rank == 0:
+    tr = reducer.trace
+    print("trace of the sink step (rank 0): main stream", torch.cuda.current_stream().cuda_stream, flush=True)
+    for t in tr:
+        if t[0] == "launch" or (t[0] == "hook" and t[1] in (0, len(reducer.buckets) - 1)):
+            print("   ", t, flush=True)
+reducer.trace = None
 g_sink2 = step(True)
-# local gradient of this rank without any reduction, averaged by hand
-reducer.direct = False
-saved_world, reducer.world = reducer.world, 1
-reducer.reset()
-out = model(ME.SparseTensor(features=f, coordinates=bc))
-point_cross_entropy(out["logits"], labels).backward()
-reducer.world = saved_world
-local_g = torch.cat([p.grad.flatten().clone() for p in model.parameters()])
+# local gradient of this rank without any reduction (through autograd's accumulation, then through the sink), averaged by hand
+saved_world = reducer.world
+
+
+def local(direct):
+    reducer.direct = direct
+    reducer.world = 1
+    reducer.reset()
+    out = model(ME.SparseTensor(features=f, coordinates=bc))
+    point_cross_entropy(out["logits"], labels).backward()
+    torch.cuda.synchronize()
+    reducer.world = saved_world
+    return torch.cat([p.grad.flatten().clone() for p in model.parameters()])
+
+
+local_g = local(False)
+local_sink = local(True)
+print(f"rank {rank}: local gradients, sink vs autograd {float((local_sink - local_g).norm() / local_g.norm()):.2e}", flush=True)
+names = [n for n, _ in model.named_parameters()]
+off = 0
+worst = []
+for n, p in model.named_parameters():
+    a, b = g_sink[off:off + p.numel()], g_hooks[off:off + p.numel()]
+    worst.append((float((a - b).norm() / b.norm().clamp_min(1e-30)), n))
+    off += p.numel()
+worst.sort(reverse=True)
+print(f"rank {rank}: parameters whose reduced gradient differs most (sink vs hooks): {worst[:6]}; {sum(1 for w in worst if w[0] > 1e-2)} of {len(worst)} above 1e-2", flush=True)
 dist.all_reduce(local_g)
 local_g /= world
 

@@ -550,6 +550,14 @@ def run_ours(args):
         e2e_host_step_ms = [1e3 * (b - a) for a, b in zip(host_t, host_t[1:])]
         assert len(loss_log) == args.steps and all(np.isfinite(loss_log)), "every timed e2e step must have delivered its loss to the host"
     clock_info = clocks.stop() if rank == 0 else None
+    if os.environ.get("GCDLSS_BENCH_PROFILE_STEP") and world == 1:
+        # ONE more step between cudaProfilerStart/Stop, outside every timed region: `ncu --profile-from-start off --metrics
+        # gpu__time_duration.sum ...` then lists exactly the launches of one steady-state step (no --launch-skip arithmetic)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident(args.steps)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     gc.enable()
 
     scans_total = scans_per_gpu * world * args.steps
@@ -562,10 +570,12 @@ def run_ours(args):
     # launches are captured and then replayed back to back on the same tensors, all launches of a class between two CUDA
     # events; the share of the step is that kernel time over the measured step time.
     roofline = None
-    # the capture step contains the gradient all-reduce, so every rank runs it; only rank 0 records and replays
+    # the capture step contains the gradient all-reduce, so every rank runs it -- through the SAME (per-launch) path: ranks on
+    # different paths complete their all-reduce buckets in different orders, and NCCL collectives issued in different orders
+    # hang (seen at 8 GPUs with GCDLSS_DDP_DIRECT=0, r2 call 18).  Only rank 0 keeps the record and replays it.
     from gcdlss_b200 import coords as gcoords
     ops.kernel_timer.captured.clear()
-    ops.kernel_timer.capture = rank == 0
+    ops.kernel_timer.capture = True
     gcoords.TABLE_LOG = []                 # every neighbour table built during the capture step (one or two coordinate managers)
     if stage == "stage2":
         harness.step(*resident[0])
@@ -574,6 +584,8 @@ def run_ours(args):
     ops.kernel_timer.capture = False
     tables, gcoords.TABLE_LOG = gcoords.TABLE_LOG, None
     torch.cuda.synchronize()
+    if rank != 0:
+        ops.kernel_timer.captured.clear()
     if rank == 0:
         pair_count = {}
         for table in tables:                             # every pointer a convolution launch may carry -> pairs of that table

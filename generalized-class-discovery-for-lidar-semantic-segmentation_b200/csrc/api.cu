@@ -24,7 +24,7 @@ struct Options {
   std::atomic<int32_t> v[GCD_OPT_COUNT_];
   Options() {
     static const struct { const char* env; int32_t dflt; } kInit[GCD_OPT_COUNT_] = {
-        {"GCD_PAIRS_FUSED", 2}, {"GCD_GATHER_FLAT", 1}, {"GCD_TC_STAGES", 0}, {"GCD_TC_GROUP", 0}, {"GCD_WG_CHUNK_MIN", 0}, {"GCD_TC_WARPS", 8}, {"GCD_BN_FUSED", 1}, {"GCD_KMAP_COOP", 0}, {"GCD_PDL", 1}, {"GCD_WGRAD_SIDE", 1}, {"GCD_DYN_TILES", 0}, {"GCD_DYN_AHEAD", 0}, {"GCD_BN_MASK_FROM_X", 1}};
+        {"GCD_PAIRS_FUSED", 2}, {"GCD_GATHER_FLAT", 1}, {"GCD_TC_STAGES", 0}, {"GCD_TC_GROUP", 0}, {"GCD_WG_CHUNK_MIN", 0}, {"GCD_TC_WARPS", 8}, {"GCD_BN_FUSED", 1}, {"GCD_KMAP_COOP", 0}, {"GCD_PDL", 1}, {"GCD_WGRAD_SIDE", 1}, {"GCD_DYN_TILES", 0}, {"GCD_DYN_AHEAD", 0}, {"GCD_BN_MASK_FROM_X", 1}, {"GCD_SCAN_LOOKBACK", 1}};
     for (int i = 0; i < GCD_OPT_COUNT_; ++i) {
       const char* e = getenv(kInit[i].env);
       v[i].store(e ? atoi(e) : kInit[i].dflt, std::memory_order_relaxed);

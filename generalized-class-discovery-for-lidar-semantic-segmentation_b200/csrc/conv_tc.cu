@@ -179,6 +179,13 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
     const char* col_base = reinterpret_cast<const char*>(p.in + chunk * 8);
     const uint32_t ld_bytes = (uint32_t)(p.ld_in * 2);   // row pitch < 4 GB: one 32 x 32 -> 64 bit multiply-add per source address
     const bool last_active = chunk * 8 < last_width;
+    // A last slice of 32 channels (Cin = 32, 96, ...) fills only half of each 128-byte operand row: with the lane mapping above
+    // half of the lanes of every copy instruction would idle.  Such a slice is gathered eight rows per instruction instead
+    // (lane = 4 chunks x 8 rows): 16 instructions per stage instead of 32, same swizzled image.
+    const bool narrow = last_width == 32;
+    const int chunk4 = lane & 3, rsub8 = lane >> 2;          // this lane's rows of a narrow slice are rsub8 + 8 j, j = 0..15
+    const uint32_t d_narrow = rsub8 * kRowBytes + ((chunk4 ^ rsub8) << 4);
+    const char* col_base4 = reinterpret_cast<const char*>(p.in + chunk4 * 8);
     const uint32_t a_base = smem_u32(smem + L.a_off);
     const uint32_t b_base = smem_u32(smem + L.b_off);
     const uint32_t b_bytes = L.b_bytes;
@@ -249,7 +256,23 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
 #ifdef GCD_TC_PROFILE
           if (!(p.ablate & 2))
 #endif
-          if (q + 1 < nq || last_active) {
+          if (q + 1 == nq && narrow) {
+            uint32_t pos = tile_base + (compact ? (uint32_t)__popc(tile_mask & ((1u << k) - 1u)) : (uint32_t)k);
+            if (pos >= (uint32_t)kRingSlices) pos -= kRingSlices;
+            const uint32_t nb = s_nbr_addr + (pos * kTileM + (uint32_t)rsub8) * 4u;
+            const uint32_t a_stage = a_base + st * kABytes + d_narrow;
+            const char* src_q = col_base4 + q * (kChunkK * 2);
+#pragma unroll
+            for (int jb = 0; jb < 16; jb += 8) {
+              if (G > 1 && ((jb >> 3) * G) >> 1 != sub) continue;     // two warps per stage: eight of the sixteen copies each
+              int r[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r[j] = lds_s32(nb + (uint32_t)(jb + j) * 32u);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                cp_async_16(a_stage + (uint32_t)(jb + j) * 1024u, src_q + (uint64_t)(uint32_t)max(r[j], 0) * ld_bytes, r[j] >= 0 ? 16u : 0u);
+            }
+          } else if (q + 1 < nq || last_active) {
             // ring position of offset k's slice: compacted tiles hold their slices in mask order
             uint32_t pos = tile_base + (compact ? (uint32_t)__popc(tile_mask & ((1u << k) - 1u)) : (uint32_t)k);
             if (pos >= (uint32_t)kRingSlices) pos -= kRingSlices;

@@ -204,6 +204,68 @@ __global__ void __launch_bounds__(kScanThreads) pairs_lookback_kernel(const int3
 }
 }  // namespace
 
+// exclusive scan of int32 in one pass (the same decoupled look-back as pairs_lookback_kernel): out[i] = sum_{j<i} in[j]
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const int32_t* in, int32_t* out, int64_t n,      // in may alias out (sort.cu)
+                                                                      unsigned long long* state, int32_t* ticket, int32_t* total_out) {
+  __shared__ int s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t base = (int64_t)tile * kLbTile + (int64_t)threadIdx.x * kLbItems;
+  int v[kLbItems];
+  int sum = 0;
+  if (base + kLbItems <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < kLbItems; i += 4) {
+      const int4 q = *reinterpret_cast<const int4*>(in + base + i);       // (in may alias out: plain loads)
+      v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kLbItems; ++i) v[i] = (base + i < n) ? in[base + i] : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < kLbItems; ++i) sum += v[i];
+  int total;
+  int pos = block_exclusive_scan(sum, &total);
+  if (threadIdx.x == 0) {
+    atomicExch(&state[tile], (tile == 0 ? kLbInclusive : kLbAggregate) | (unsigned)total);
+    if (tile == 0) s_prefix = 0;
+  }
+  if (tile > 0 && threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int prefix = 0;
+    for (int look = tile - 1;; look -= 32) {
+      const int t = look - lane;
+      unsigned long long st = kLbInclusive;
+      if (t >= 0) {
+        do { st = *reinterpret_cast<volatile unsigned long long*>(&state[t]); } while ((st >> 32) == 0);
+      }
+      const unsigned incl = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const int first = incl ? __ffs(incl) - 1 : 32;
+      int val = lane <= first ? (int)(unsigned)st : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+      prefix += val;
+      if (incl) break;
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&state[tile], kLbInclusive | (unsigned)(prefix + total));
+      s_prefix = prefix;
+    }
+  }
+  __syncthreads();
+  pos += s_prefix;
+  const bool last_tile = base <= n - 1 && n - 1 < base + kLbItems;     // this thread holds the last element
+#pragma unroll
+  for (int i = 0; i < kLbItems; ++i) {
+    if (base + i < n) out[base + i] = pos;
+    pos += v[i];
+  }
+  if (last_tile && total_out) *total_out = pos;                        // v[i] = 0 beyond n: pos is the grand total
+}
+
 size_t pairs_lookback_workspace_bytes(int64_t total_entries) {
   return align_up((size_t)(ceil_div(total_entries > 0 ? total_entries : 1, kLbTile)) * 8 + 8, 256);
 }
@@ -252,6 +314,18 @@ int32_t exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* 
   if (workspace_bytes < scan_workspace_bytes(n)) {
     set_error("exclusive_scan_i32: workspace too small");
     return GCD_ERR_WORKSPACE;
+  }
+  if (option(GCD_OPT_SCAN_LOOKBACK)) {
+    // one pass: scan_workspace_bytes(n) (4 bytes per 1024 elements, 256-byte granules) always covers 8 bytes per 4096 + a ticket
+    const int64_t lb_tiles = ceil_div(n, kLbTile);
+    const size_t need = (size_t)lb_tiles * 8 + 8;
+    if (need <= workspace_bytes) {
+      if (const cudaError_t e = cudaMemsetAsync(workspace, 0, need, stream); e != cudaSuccess) return cuda_fail(e, "exclusive_scan_i32(memset)");
+      unsigned long long* state = static_cast<unsigned long long*>(workspace);
+      scan_lookback_kernel<<<(unsigned)lb_tiles, kScanThreads, 0, stream>>>(in, out, n, state, reinterpret_cast<int32_t*>(state + lb_tiles), total);
+      GCD_LAUNCH_CHECK("exclusive_scan_i32(look-back)");
+      return GCD_OK;
+    }
   }
   int32_t* sums = static_cast<int32_t*>(workspace);
   const int64_t n_tiles = ceil_div(n, kScanTile);

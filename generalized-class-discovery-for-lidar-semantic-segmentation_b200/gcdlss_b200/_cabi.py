@@ -19,7 +19,7 @@ F32, BF16 = 0, 1
 MATH_FP32_SIMT, MATH_BF16_TC = 0, 1
 ROUND_FLOOR, ROUND_HALF_EVEN = 0, 1
 DEV_KEY_RANGE, DEV_DUPLICATE, DEV_TABLE_FULL = 1, 2, 4
-OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN, OPT_TC_WARPS, OPT_BN_FUSED, OPT_KMAP_COOP, OPT_PDL, OPT_WGRAD_SIDE, OPT_DYN_TILES, OPT_DYN_AHEAD, OPT_BN_MASK_FROM_X = range(13)
+OPT_PAIRS_FUSED, OPT_GATHER_FLAT, OPT_TC_STAGES, OPT_TC_GROUP, OPT_WG_CHUNK_MIN, OPT_TC_WARPS, OPT_BN_FUSED, OPT_KMAP_COOP, OPT_PDL, OPT_WGRAD_SIDE, OPT_DYN_TILES, OPT_DYN_AHEAD, OPT_BN_MASK_FROM_X, OPT_SCAN_LOOKBACK = range(14)
 
 
 def build(force: bool = False) -> str:

@@ -102,7 +102,9 @@ typedef enum {
   GCD_OPT_BN_MASK_FROM_X = 12, /* 1 (default): the fused batch-norm backward of conv -> BN -> ReLU units inside gcd_block_backward re-derives
                                   the ReLU mask from the convolution output (x * scale + shift > 0, the forward pass's own arithmetic)
                                   and does not read the stored activation; 0: reads it */
-  GCD_OPT_COUNT_ = 13
+  GCD_OPT_SCAN_LOOKBACK = 13, /* 1 (default): the device-wide exclusive scans behind gcd_unique_rows / gcd_coords_stride2 run as one
+                                 decoupled-look-back launch; 0: three launches (tile scan, scan of the tile sums, add) */
+  GCD_OPT_COUNT_ = 14
 } gcd_option;
 int32_t gcd_set_option(int32_t option, int32_t value);
 int32_t gcd_get_option(int32_t option);

@@ -18,6 +18,13 @@ constexpr int kFusedBwdMaxChannels = 512;      // two-phase backward kernel: six
 // mask the forward pass applied if both sides compute scale and shift to the same bits.
 __device__ __forceinline__ float bn_scale_of(float g, float is) { return __fmul_rn(g, is); }
 __device__ __forceinline__ float bn_shift_of(float b, float m, float g, float is) { return __fmaf_rn(-__fmul_rn(m, g), is, b); }
+// dx of the batch-norm backward, likewise with explicit roundings: the two-phase kernels (two template variants) and the
+// stand-alone pass inline this into different surroundings, and the fma contraction ptxas chooses must not differ between them
+// (the C-sequenced blocks and the per-launch path are held bit-identical in bf16, tests/test_gpu_fused_block.py)
+__device__ __forceinline__ float bn_dx_of(float g, float x, float k, float mean, float is, float sg, float sgx) {
+  const float xhat = __fmul_rn(__fsub_rn(x, mean), is);
+  return __fmul_rn(k, __fsub_rn(__fsub_rn(g, sg), __fmul_rn(xhat, sgx)));
+}
 
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
@@ -502,8 +509,7 @@ __device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy,
     for (int j = 0; j < V; ++j) {
       const int ch = a.g * V + j;
       if (relu && !(ya[j] > 0.f)) ga[j] = 0.f;
-      const float xhat = (xa[j] - s_mean[ch]) * s_is[ch];
-      o[j] = s_k[ch] * (ga[j] - s_sg[ch] - xhat * s_sgx[ch]);
+      o[j] = bn_dx_of(ga[j], xa[j], s_k[ch], s_mean[ch], s_is[ch], s_sg[ch], s_sgx[ch]);
     }
     VecW<T>::store(dx + a.r * ld_dx + a.g * V, o);
     if (dres) VecW<T>::store(dres + a.r * ld_dres + a.g * V, ga);
@@ -512,8 +518,7 @@ __device__ __forceinline__ void bn_bwd_apply_wide_body(const T* __restrict__ dy,
       for (int j = 0; j < V; ++j) {
         const int ch = b.g * V + j;
         if (relu && !(yb[j] > 0.f)) gb[j] = 0.f;
-        const float xhat = (xb[j] - s_mean[ch]) * s_is[ch];
-        o[j] = s_k[ch] * (gb[j] - s_sg[ch] - xhat * s_sgx[ch]);
+        o[j] = bn_dx_of(gb[j], xb[j], s_k[ch], s_mean[ch], s_is[ch], s_sg[ch], s_sgx[ch]);
       }
       VecW<T>::store(dx + b.r * ld_dx + b.g * V, o);
       if (dres) VecW<T>::store(dres + b.r * ld_dres + b.g * V, gb);

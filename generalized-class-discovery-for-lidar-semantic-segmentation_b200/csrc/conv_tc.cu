@@ -94,7 +94,10 @@ __host__ __device__ inline SmemLayout make_layout(int stages, int n_tile_cols) {
 // kPerm (tile-sorted tables, tilesort.cu): table column i is output row p.out_rows[i]; only the epilogue's store address changes.
 // kPW = gather warps (8, or 16: two warps per ring slot; the gather is issue-bound per warp at ~90 cycles per warp-level copy,
 // the LSU takes one every ~8): warps [0, kPW) gather, [kPW, kPW + 4) epilogue, kPW + 4 MMA, kPW + 5 table.
-template <int kNQ, bool kPerm = false, int kPW = kProducerWarps>
+// kDyn: dynamic tile schedule (p.sched).  A template parameter, not a run-time flag: with the choice made at run time the MMA
+// warp's loop state (stage index, phase, both descriptors) fell out of the uniform registers -- 31 instead of 13 R2UR in the
+// SASS, every MMA preceded by five of them -- and the statically scheduled kernel lost 5 % (r2 calls 9-19).
+template <int kNQ, bool kPerm = false, int kPW = kProducerWarps, bool kDyn = false>
 __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const FwdParams p) {
   constexpr int kEpi0 = kPW, kMma = kPW + 4, kTab = kPW + 5;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
   // keeps the rows with many neighbours at its end).  A CTA that becomes resident late -- another kernel (NCCL, a weight
   // gradient on a second stream) holds its SM -- then finds little or nothing left instead of running its fixed share as a
   // second wave, and tiles of very different cost (1 .. 27 offsets in a sorted table) balance themselves.
-  const bool dyn = p.sched != nullptr;
+  constexpr bool dyn = kDyn;
   auto static_work = [&](uint32_t seq) -> int64_t {
     const int64_t w = (int64_t)blockIdx.x + (int64_t)seq * gridDim.x;
     return w < n_work ? w : -1;
@@ -477,7 +480,12 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
     long long prof_full = 0, prof_acc = 0; const long long prof_t0 = clock64();
 #endif
     for (;; ++tile_seq) {
-      if ((dyn ? published_work(tile_seq) : static_work(tile_seq)) < 0) break;
+      if constexpr (kDyn) {
+        const bool done = published_work(tile_seq) < 0;
+        if (__all_sync(0xffffffffu, done)) break;
+      } else {
+        if (static_work(tile_seq) < 0) break;
+      }
       const uint32_t buf = tile_seq & 1;
 #ifdef GCD_TC_PROFILE
       const long long ca0 = clock64();
@@ -530,7 +538,8 @@ __global__ void __launch_bounds__((kPW + 6) * 32, 1) conv_fwd_tc_kernel(const Fw
     long long prof_ewait = 0; const long long prof_t0 = clock64();
 #endif
     for (;; ++tile_seq) {
-      const int64_t work = dyn ? published_work(tile_seq) : static_work(tile_seq);
+      int64_t work;
+      if constexpr (kDyn) work = published_work(tile_seq); else work = static_work(tile_seq);
       if (work < 0) break;
       const int64_t tm = work / p.n_tiles_n;
       const int tn = (int)(work - tm * p.n_tiles_n);
@@ -955,15 +964,15 @@ bool conv_forward_tc_supported(const gcd_conv_args* a) {
 }
 
 using FwdKernel = void (*)(const FwdParams);
-template <bool kPerm, int kPW = kProducerWarps>
+template <bool kPerm, int kPW = kProducerWarps, bool kDyn = false>
 FwdKernel pick_fwd_kernel(int nq) {
   switch (nq) {
-    case 1: return conv_fwd_tc_kernel<1, kPerm, kPW>;
-    case 2: return conv_fwd_tc_kernel<2, kPerm, kPW>;
-    case 3: return conv_fwd_tc_kernel<3, kPerm, kPW>;
-    case 4: return conv_fwd_tc_kernel<4, kPerm, kPW>;
-    case 6: return conv_fwd_tc_kernel<6, kPerm, kPW>;
-    default: return conv_fwd_tc_kernel<0, kPerm, kPW>;
+    case 1: return conv_fwd_tc_kernel<1, kPerm, kPW, kDyn>;
+    case 2: return conv_fwd_tc_kernel<2, kPerm, kPW, kDyn>;
+    case 3: return conv_fwd_tc_kernel<3, kPerm, kPW, kDyn>;
+    case 4: return conv_fwd_tc_kernel<4, kPerm, kPW, kDyn>;
+    case 6: return conv_fwd_tc_kernel<6, kPerm, kPW, kDyn>;
+    default: return conv_fwd_tc_kernel<0, kPerm, kPW, kDyn>;
   }
 }
 
@@ -980,6 +989,8 @@ static cudaError_t tc_kernels_opt_in() {
       opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<true>(nq)));
       opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<false, 16>(nq)));
       opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<true, 16>(nq)));
+      opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<false, kProducerWarps, true>(nq)));
+      opt_in(reinterpret_cast<const void*>(pick_fwd_kernel<true, kProducerWarps, true>(nq)));
     }
     opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<1>));
     opt_in(reinterpret_cast<const void*>(conv_wgrad_tc_kernel<2>));
@@ -1030,8 +1041,10 @@ int32_t conv_forward_tc(const gcd_conv_args* a, cudaStream_t st) {
   const SmemLayout L = make_layout(stages, p.n_tile_cols);
   const size_t smem = L.total + 1024;
   const int nq_sel = (a->c_in + kChunkK - 1) / kChunkK;
+  if (pw == 16) p.sched = nullptr;      // (the sixteen-warp tuning variant exists with the static schedule only)
   const FwdKernel kernel = pw == 16 ? (p.out_rows ? pick_fwd_kernel<true, 16>(nq_sel) : pick_fwd_kernel<false, 16>(nq_sel))
-                                    : (p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel));
+                           : p.sched ? (p.out_rows ? pick_fwd_kernel<true, kProducerWarps, true>(nq_sel) : pick_fwd_kernel<false, kProducerWarps, true>(nq_sel))
+                                     : (p.out_rows ? pick_fwd_kernel<true>(nq_sel) : pick_fwd_kernel<false>(nq_sel));
   if (const cudaError_t e = tc_kernels_opt_in(); e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcgen05 kernels)");
   if (a->c_in > 16 * kChunkK) { set_error("conv_forward_tc: more than 1024 input channels unsupported"); return GCD_ERR_UNSUPPORTED; }
   const int64_t n_work = ceil_div(a->n_out, kTileM) * p.n_tiles_n;

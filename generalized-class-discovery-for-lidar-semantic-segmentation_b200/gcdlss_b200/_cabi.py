@@ -30,11 +30,22 @@ def build(force: bool = False) -> str:
         env = dict(os.environ)
         env["PATH"] = env.get("PATH", "") + ":/usr/local/cuda/bin"
         cmd = ["make", "-C", _CSRC, "-j", str(min(8, os.cpu_count() or 1))]
-        if force:
-            subprocess.run(["make", "-C", _CSRC, "clean"], env=env, check=True, capture_output=True)
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("building libgcdlss_sm100a.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+        # one builder at a time: under torchrun every rank imports the package, and N concurrent `make`s in the same build
+        # directory could leave a rank loading a half-written library.  The others wait for the lock and then find it fresh.
+        import fcntl
+        os.makedirs(os.path.join(_CSRC, "build"), exist_ok=True)
+        with open(os.path.join(_CSRC, "build", ".lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or not os.path.exists(LIB_PATH) or _stale():
+                    if force:
+                        subprocess.run(["make", "-C", _CSRC, "clean"], env=env, check=True, capture_output=True)
+                        os.makedirs(os.path.join(_CSRC, "build"), exist_ok=True)
+                    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+                    if r.returncode != 0:
+                        raise RuntimeError("building libgcdlss_sm100a.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

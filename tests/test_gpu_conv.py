@@ -99,15 +99,18 @@ def test_layer_forward_backward(cuda, math_mode, mode, case):
         assert v < tol, (k, v)
 
 
+# c = 96: the 16-byte-wide kernels (what a MinkUNet runs); c = 20: the 8-byte "vec" generation in bf16 (20 % 8 != 0), still wide in fp32;
+# c = 17: the element-wise generation in both (the fallback chain of csrc/bn.cu, bn.cu:gcd_bn_*)
+@pytest.mark.parametrize("c", [96, 20, 17])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("training,relu,residual", [(True, True, True), (True, False, False), (False, True, False), (True, True, False)])
-def test_batchnorm_fused(cuda, math_mode, mode, training, relu, residual):
+def test_batchnorm_fused(cuda, math_mode, mode, training, relu, residual, c):
     import MinkowskiEngine as ME
     math_mode(mode)
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     tol = TOL_FP32 if mode == "fp32" else TOL_BF16
     bc, _ = _scene(3, 2000)
-    n, c = bc.shape[0], 96
+    n = bc.shape[0]
     rng = np.random.default_rng(2)
     x_np = (rng.normal(0.3, 2.0, (n, c))).astype(np.float32)
     r_np = rng.normal(0, 1, (n, c)).astype(np.float32)

@@ -107,7 +107,8 @@ class ClockSampler:
 
 class NvmlClockSampler:
     """The same samples through NVML in-process (nvidia_ml_py): a thread reads the SM clock and the clocks-event reasons every
-    25 ms.  An `nvidia-smi -lms` child process re-queries the driver from outside on every poll, and every poll that fell into
+    100 ms (each NVML query takes 10-50 ms of driver time on this box, tools/nvml_probe.py: a faster poll keeps the driver busy
+    for no gain).  An `nvidia-smi -lms` child process re-queries the driver from outside on every poll, and every poll that fell into
     the timed region showed up as one step of 25-60 ms among 20 steps of 9.6 ms (r2 call 10: mean 10.8-11.1 ms against a
     median of 9.5-9.7 ms); NVML calls from inside the process do not stall the launch path."""
 
@@ -140,7 +141,7 @@ class NvmlClockSampler:
                 self.samples.append((time.perf_counter(), float(mhz), int(reasons)))
             except Exception:       # noqa: BLE001  (a failed sample is a missing sample)
                 pass
-            time.sleep(0.025)
+            time.sleep(0.1)
 
     def wait_ready(self, timeout=5.0):
         t0 = time.perf_counter()

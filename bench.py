@@ -547,7 +547,9 @@ def run_ours(args):
         gc.collect()
         warm_up(step_e2e, finish_e2e)          # the e2e path allocates its own shapes: same warm-up rule as above
         loss_log.clear()
+        seg0 = torch.cuda.memory_stats().get("segment.all.allocated", 0)
         e2e_ms, e2e_step_ms = timed(step_e2e, args.steps, finish_e2e)
+        e2e_new_segments = torch.cuda.memory_stats().get("segment.all.allocated", 0) - seg0      # cudaMalloc calls inside the timed e2e region
         e2e_host_step_ms = [1e3 * (b - a) for a, b in zip(host_t, host_t[1:])]
         assert len(loss_log) == args.steps and all(np.isfinite(loss_log)), "every timed e2e step must have delivered its loss to the host"
     clock_info = clocks.stop() if rank == 0 else None
@@ -651,6 +653,7 @@ def run_ours(args):
         print("step_ms e2e:     ", " ".join(f"{v:.2f}" for v in e2e_step_ms), file=sys.stderr)
         if not args.no_e2e:
             print("host_ms e2e:     ", " ".join(f"{v:.2f}" for v in e2e_host_step_ms), file=sys.stderr)
+            print("e2e allocator segments allocated inside the timed region:", e2e_new_segments, file=sys.stderr)
 
     descr = {"stage1": ("MinkUNet34RC backbone + final head (Stage-1 MinkUNetBase, ref modules/exp.py:249-267)",
                         "hash + kernel maps (side stream, one batch ahead) + fwd + CE + bwd + grad all-reduce + SGD"),

@@ -675,7 +675,7 @@ class TrunkFunction(torch.autograd.Function):
         # its reset()), nothing is returned to autograd for those parameters, and the reducer is told per network stage -- with
         # an event the library records behind the stage's kernels -- which gradients are final, so the all-reduce of a bucket
         # starts while the rest of the backward pass is still running.
-        sink = ops.grad_sink() if dev.type == "cuda" else None
+        sink = ops.grad_sink() if (dev.type == "cuda" or ops.SINK_ON_HOST) else None
         sink_ptrs = None
         if sink is not None:
             sink_ptrs = [sink.grad_ptr(p) for p in plan.parameters()]

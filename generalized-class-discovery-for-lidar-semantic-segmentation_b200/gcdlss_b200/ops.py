@@ -98,6 +98,7 @@ exec_contexts = _ExecContexts()
 # Gradient sink: a data-parallel reducer (ddp.GradBucketReducer) registers itself here; the trunk's backward pass then lets
 # the kernels accumulate parameter gradients straight into the reducer's buckets (functional.TrunkFunction.backward).
 _grad_sink = {"ref": None}
+SINK_ON_HOST = False        # CPU plumbing tests only (tests/test_trunk_plumbing.py): let the sink see host tensors
 
 
 def set_grad_sink(sink) -> None:

@@ -196,6 +196,11 @@ def run_ops(prog, n_ops, stream, launches):
             if o.op == 3:
                 src = src + _load(o.dst, o.n, o.c, o.ld_dst, o.dtype)
             _store(o.dst, o.n, o.c, o.ld_dst, o.dtype, src)
+        elif o.op == 4:                     # GCD_OP_RECORD_EVENT: nothing to order on the host; the test reads the order from this log
+            recorded_events.append(int(o.dst))
         else:
             raise ValueError(f"unknown op {o.op}")
     return 0
+
+
+recorded_events = []

@@ -114,3 +114,74 @@ def test_trunk_function_against_autograd(trunk_env, arch, taps):
         torch.testing.assert_close(got.double(), p.grad.double(), rtol=2e-3, atol=2e-4 * max(float(p.grad.abs().max()), 1e-6), msg=lambda m: f"{name}: {m}")
         checked += 1
     assert checked == 3 * len(plan.units)
+
+
+def test_gradient_sink_plumbing(trunk_env, monkeypatch):
+    """functional.TrunkFunction.backward with a gradient sink (ddp.GradBucketReducer on more than one GPU): the kernels -- here
+    their host emulation -- accumulate straight into the reducer's flat buckets, autograd gets no gradient for the trunk's
+    parameters, one event per network stage is recorded in the order the stages finish, and the reducer launches every bucket
+    exactly once, behind the event of the last stage that touched it; the bucket that also holds a parameter in front of the
+    trunk (the stem) leaves only when that parameter's own hook has fired.  The buckets must hold the gradients of the plain path."""
+    import gcdlss_b200
+    from gcdlss_b200 import ops
+    from gcdlss_b200.ddp import GradBucketReducer
+    from gcdlss_b200.nn import run_trunk, trunk_plan
+    from gcdlss_b200.sparse_tensor import CoordinateMapKey, SparseTensor
+    from models import minkunet as mu
+
+    class FakeEvent:
+        n = 0
+
+        def __init__(self):
+            FakeEvent.n += 1
+            self.cuda_event = 1000 + FakeEvent.n
+
+    torch.manual_seed(0)
+    model = mu.MinkUNet14A(1, 17).train()
+    enc = [(getattr(model, c), getattr(model, b), getattr(model, k)) for c, b, k in mu._ENCODER]
+    dec = [(getattr(model, c), getattr(model, b), getattr(model, k)) for c, b, k in mu._DECODER]
+    plan = trunk_plan(enc, dec)
+    stem_w = torch.nn.Parameter(torch.ones(32))          # stands for the stem: in front of the trunk, its gradient arrives last
+    head_w = torch.nn.Parameter(torch.ones(96))          # stands for the head: behind the trunk, its gradient arrives first
+    bc = np.concatenate([small_cloud(61, 1200, spread=0.5, batch=0), small_cloud(62, 700, spread=0.5, batch=1)])
+    x0 = torch.randn(bc.shape[0], 32)
+    params = [stem_w] + plan.parameters() + [head_w]     # registration order of a model: stem first, head last
+
+    def run():
+        mgr = trunk_env(torch.from_numpy(bc))
+        stages = run_trunk(plan, SparseTensor(x0 * stem_w, coordinate_map_key=CoordinateMapKey(1), coordinate_manager=mgr))
+        out = stages[7].F * head_w
+        (out * torch.linspace(-1, 1, out.numel()).view_as(out)).sum().backward()
+        return torch.cat([p.grad.flatten().clone() for p in params])
+
+    plain = run()
+    for p in params:
+        p.grad = None
+    red = GradBucketReducer(params, bucket_bytes=1 << 20)        # a handful of buckets
+    assert len(red.buckets) >= 3
+    launched = []
+    red.world = 2
+    red._launch = lambda b, gate=None: launched.append((b, getattr(gate, "cuda_event", None))) or len(launched)
+    events = {}
+    monkeypatch.setattr(red, "stage_event", lambda i: events.setdefault(i, FakeEvent()))
+    monkeypatch.setattr(ops, "SINK_ON_HOST", True)
+    ops.set_grad_sink(red)
+    emu_ops.recorded_events.clear()
+    try:
+        red.reset()
+        sunk = run()
+    finally:
+        ops.set_grad_sink(None)
+    # eight stage events, recorded in the order the stages finish
+    assert len(emu_ops.recorded_events) == 8 and len(set(emu_ops.recorded_events)) == 8
+    # every bucket went out exactly once; all but the one that holds the stem behind a stage event, in the order of those events
+    assert sorted(b for b, _ in launched) == list(range(len(red.buckets))), launched
+    stem_bucket = red._owner[stem_w]
+    gated = [(b, e) for b, e in launched if e is not None]
+    assert len(gated) == len(red.buckets) - 1 and all(e in emu_ops.recorded_events for _, e in gated)
+    order = [emu_ops.recorded_events.index(e) for _, e in gated]
+    assert order == sorted(order)
+    assert dict(launched)[stem_bucket] is None and launched[-1][0] == stem_bucket, "the stem's bucket leaves last, from the stem's own hook"
+    assert red._pending == [0] * len(red.buckets)
+    # same gradients as the plain path (the buckets ARE the .grad tensors)
+    torch.testing.assert_close(sunk, plain, rtol=1e-4, atol=1e-6 * float(plain.abs().max()))
